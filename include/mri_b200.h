@@ -1,0 +1,132 @@
+/* mri_b200.h - C ABI of the B200-native coordinate-network hot path.
+ *
+ * Drop-in boundary for Benjamin-Fouquet/mri_interpolation.  The reference has no FFI
+ * layer: its hot path is the torch arithmetic inside the nn.Module classes of
+ * encoding.py / models.py.  Each entry point below replaces one such piece (cited
+ * as reference file:line); the Python classes in mri_interpolation_b200/ keep the
+ * reference's constructor/forward surface and bind these symbols through ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; buffers are owned by the caller;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*);
+ *     no hidden synchronisation, no allocation, re-entrant across streams/devices;
+ *   - return value: 0 = ok, <0 = mri_status error; mri_last_error() gives the message
+ *     (thread-local); nothing throws or exits across this boundary;
+ *   - row-major fp32 tensors, coordinates (n, dim), encodings (n, n_levels*n_features).
+ */
+#ifndef MRI_B200_H
+#define MRI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRI_B200_VERSION 100
+#define MRI_MAX_DIM 4      /* hash grid input dims supported by the kernels: 2, 3, 4 (x,y,z,t) */
+#define MRI_MAX_LEVELS 32
+
+enum mri_status {
+  MRI_OK = 0,
+  MRI_ERR_INVALID = -1,     /* bad argument (null pointer, negative size, ...) */
+  MRI_ERR_UNSUPPORTED = -2, /* shape / dim / feature count without a kernel */
+  MRI_ERR_CUDA = -3         /* CUDA runtime error (message in mri_last_error) */
+};
+
+enum mri_activation {
+  MRI_ACT_IDENTITY = 0,
+  MRI_ACT_SINE = 1, /* sin(w0 * pre)          models.py:108-114 */
+  MRI_ACT_GELU = 2, /* exact erf GELU         nn.GELU default, models.py:672 */
+  MRI_ACT_RELU = 3  /* BaseMLP default stack  models.py:31 */
+};
+
+/* One resolution level of the multiresolution hash grid.
+ * encoding.py:81-96 (_HashGrid) / 194-214 (_HashGridV2): per-axis resolution (V1: all
+ * equal), `rows` = hashmap_size (table rows, each n_features floats), `offset` = position
+ * of the level's table inside the flat table arena, in floats. */
+typedef struct mri_level {
+  float resolution[MRI_MAX_DIM];
+  uint32_t rows;
+  uint32_t reserved;
+  uint64_t offset;
+} mri_level_t;
+
+int mri_version(void);
+const char* mri_last_error(void);
+/* number of SMs of the current device (grid sizing on the host side) */
+int mri_sm_count(void);
+
+/* ---- multiresolution hash grid ------------------------------------------------------- */
+
+/* Forward of MultiResHashGrid / MultiResHashGridV2: encoding.py:108-128 (per level) and
+ * :190-191 (concat).  out[i, l*F + f] = sum_c tables[level l][hash(corner c)][f] * w_c. */
+int mri_hashgrid_forward(const float* x, int64_t n, int dim, const float* tables,
+                         const mri_level_t* host_levels, int n_levels, int n_features,
+                         float* out, void* stream);
+
+/* Backward w.r.t. the tables (autograd of encoding.py:127-128): grad_tables[h_c] += w_c *
+ * grad_out, ACCUMULATING into grad_tables (same arena layout as `tables`; caller zero-fills). */
+int mri_hashgrid_backward(const float* x, int64_t n, int dim, const float* grad_out,
+                          float* grad_tables, const mri_level_t* host_levels, int n_levels,
+                          int n_features, void* stream);
+
+/* Parity probe: corner hashes (n, L, 2^dim) uint32 and weights (n, L, 2^dim) f32 in the
+ * reference's corner order (encoding.py:69-78, 101-106, 121-124). Either output may be NULL. */
+int mri_hashgrid_corners(const float* x, int64_t n, int dim, const mri_level_t* host_levels,
+                         int n_levels, uint32_t* hashes, float* weights, void* stream);
+
+/* ---- dense layers (SIREN layer / decoder Linear) ---------------------------------------- */
+
+/* y = act(x W^T + b): SirenLayer.forward models.py:153-156, decoder Linear+GELU
+ * models.py:730-736.  x (n,k) row stride ldx; W (m,k); b (m) or NULL; y (n,m).
+ * `pre` (n,m) or NULL receives the pre-activation needed by mri_dense_backward. */
+int mri_dense_forward(const float* x, int64_t ldx, const float* w, const float* b, int64_t n,
+                      int k, int m, int act, float w0, float* y, float* pre, void* stream);
+
+/* Backward of the layer above.  dpre = grad_y * act'(pre) is written to `dpre` (n,m scratch);
+ * grad_w (m,k) += dpre^T x; grad_b (m) += sum_n dpre; grad_x (n,k) = dpre W (skipped if NULL).
+ * grad_b may be NULL. */
+int mri_dense_backward(const float* x, int64_t ldx, const float* w, const float* pre,
+                       const float* grad_y, int64_t n, int k, int m, int act, float w0,
+                       float* dpre, float* grad_x, float* grad_w, float* grad_b, void* stream);
+
+/* ---- loss / optimiser ------------------------------------------------------------------ */
+
+/* F.mse_loss(y, y_pred) (models.py:64): *loss += sum((pred-target)^2) * inv_count and
+ * grad_pred = 2 (pred-target) * inv_count; caller zeroes *loss; grad_pred may be NULL.
+ * inv_count = 1/numel of the GLOBAL batch (data-parallel ranks pass the global count). */
+int mri_mse_loss_grad(const float* pred, const float* target, int64_t count, float inv_count,
+                      float* grad_pred, float* loss, void* stream);
+
+/* One dense torch.optim.Adam step (models.py:68-70) over a flat parameter arena.
+ * step is 1-based; hyper-parameters are doubles like torch's python floats (bias corrections
+ * are evaluated in double on the host); weight_decay is torch's coupled L2 term.  grad_scale multiplies g first
+ * (1.0 normally).  If zero_grad != 0 the gradient is cleared in the same pass. */
+int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t step, double lr,
+                  double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                  int zero_grad, void* stream);
+
+/* ---- dense-grid sweep -------------------------------------------------------------------- */
+
+/* Coordinates of voxels [first, first+count) of a C-order grid of `shape` (launcher.py:191-202,
+ * utils.py:14-23): coords[i, d] = axis_d[idx_d].  `axes` = concatenated per-axis value vectors
+ * (the caller passes torch.linspace output so the floats are bit-identical to the reference). */
+int mri_grid_coords(const float* axes, const int32_t* host_shape, int dim, int64_t first,
+                    int64_t count, float* coords, void* stream);
+
+/* Fused sweep of a hash-grid + MLP-decoder model (models.py:741-751 intended forward, nb cell 37):
+ * voxel index -> coordinates -> all-level encoding -> decoder, nothing but `out` (count x m_out)
+ * is written.  Decoder = n_dense layers of Linear+act, parameters packed as
+ * [W0 (m0,k0) | b0 (m0) | W1 | b1 ...] in `decoder`; host_dims = [k0, m0, m1, ...]. */
+int mri_hashmlp_sweep(const float* axes, const int32_t* host_shape, int dim, int64_t first,
+                      int64_t count, const float* tables, const mri_level_t* host_levels,
+                      int n_levels, int n_features, const float* decoder, const int32_t* host_dims,
+                      int n_dense, int act, int last_act, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRI_B200_H */

@@ -1,0 +1,78 @@
+"""Build libmri_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m mri_interpolation_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels with the repo
+snapshot to the GPU box.  No torch headers are involved: the ABI is plain C (include/mri_b200.h).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libmri_b200.so")
+SOURCES = ["core.cu", "hashgrid.cu", "dense.cu", "optim.cu", "sweep.cu", "siren_tc.cu"]
+HEADERS = ["common.cuh", "../../include/mri_b200.h"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+
+
+def up_to_date() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return False
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {os.path.basename(src)}\n{out}")
+        if p.returncode != 0:
+            failed = True
+    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if failed or verbose:
+        sys.stderr.write("\n".join(log) + "\n")
+    if failed:
+        raise RuntimeError("nvcc failed, see log above")
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", LIB_PATH,
+            *objs]
+    subprocess.run(link, check=True)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

@@ -1,0 +1,281 @@
+// Multiresolution hash-grid encoding kernels for sm_100a (B200).
+//
+//   hashgrid_fwd_kernel   K1: all corners of one (coordinate, level) per thread, gathers issued
+//                         back-to-back (2^D independent LDG.64/128 in flight per thread), no
+//                         intermediates in memory.  grid = (ceil(n/256), L): blocks are scheduled
+//                         level-major so one level's table is the L2/L1 working set at a time.
+//   hashgrid_bwd_kernel   K2: recomputes hashes/weights and scatters w*dOut with vector
+//                         reductions red.global.add.v2/v4.f32 (SASS REDG.E.ADD.F32x2/x4).
+//   hashgrid_corners_kernel  parity probe: dumps hashes and weights in the reference's corner order.
+//
+// Arithmetic follows encoding.py:108-128 (see common.cuh::make_cell); hash indices are bit-exact.
+#include "common.cuh"
+
+namespace mri {
+
+namespace {
+
+template <int F>
+struct Feat {
+  float v[F];
+};
+
+template <int F>
+__device__ __forceinline__ Feat<F> gather_row(const float* __restrict__ row) {
+  Feat<F> r;
+  if constexpr (F == 1) {
+    r.v[0] = __ldg(row);
+  } else if constexpr (F == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(row));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(row) + q);
+      r.v[4 * q + 0] = t.x; r.v[4 * q + 1] = t.y; r.v[4 * q + 2] = t.z; r.v[4 * q + 3] = t.w;
+    }
+  }
+  return r;
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_row(float* row, const Feat<F>& g, float w) {
+  if constexpr (F == 1) {
+    red_add_f32(row, g.v[0] * w);
+  } else if constexpr (F == 2) {
+    red_add_v2(row, g.v[0] * w, g.v[1] * w);
+  } else {
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q)
+      red_add_v4(row + 4 * q, g.v[4 * q] * w, g.v[4 * q + 1] * w, g.v[4 * q + 2] * w, g.v[4 * q + 3] * w);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void store_feat(float* dst, const Feat<F>& a) {
+  if constexpr (F == 1) {
+    dst[0] = a.v[0];
+  } else if constexpr (F == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(a.v[0], a.v[1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < F / 4; ++q)
+      reinterpret_cast<float4*>(dst)[q] = make_float4(a.v[4 * q], a.v[4 * q + 1], a.v[4 * q + 2], a.v[4 * q + 3]);
+  }
+}
+
+template <int D, int F, bool POW2>
+__device__ __forceinline__ Feat<F> encode_one_level(const Cell<D>& cell, const LevelDev& lv, const float* __restrict__ tbl) {
+  constexpr int C = 1 << D;
+  Feat<F> rows[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const uint32_t h = wrap_rows<POW2>(corner_hash<D>(cell, c), lv);
+    rows[c] = gather_row<F>(tbl + static_cast<size_t>(h) * F);
+  }
+  Feat<F> acc;
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc.v[f] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {  // ascending corner order, like torch.sum over dim=-2
+    const float w = corner_weight<D>(cell, c);
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc.v[f] = fmaf(rows[c].v[f], w, acc.v[f]);
+  }
+  return acc;
+}
+
+template <int D, int F>
+__global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const float* __restrict__ x, const float* __restrict__ tables,
+                                                           const __grid_constant__ LevelTable T, int64_t n,
+                                                           int out_stride, float* __restrict__ out) {
+  const int level = blockIdx.y;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const LevelDev& lv = T.lv[level];
+  float xv[D];
+  load_coord<D>(x, i, xv);
+  const Cell<D> cell = make_cell<D>(xv, lv);
+  const float* __restrict__ tbl = tables + lv.offset;
+  const Feat<F> acc = lv.is_pow2 ? encode_one_level<D, F, true>(cell, lv, tbl) : encode_one_level<D, F, false>(cell, lv, tbl);
+  store_feat<F>(out + i * out_stride + level * F, acc);
+}
+
+template <int D, int F>
+__global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grad_out,
+                                                           const __grid_constant__ LevelTable T, int64_t n,
+                                                           int out_stride, float* __restrict__ grad_tables) {
+  constexpr int C = 1 << D;
+  const int level = blockIdx.y;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const LevelDev& lv = T.lv[level];
+  float xv[D];
+  load_coord<D>(x, i, xv);
+  const Cell<D> cell = make_cell<D>(xv, lv);
+  float* tbl = grad_tables + lv.offset;
+  const Feat<F> g = gather_row<F>(grad_out + i * out_stride + level * F);
+  if (lv.is_pow2) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t h = wrap_rows<true>(corner_hash<D>(cell, c), lv);
+      scatter_row<F>(tbl + static_cast<size_t>(h) * F, g, corner_weight<D>(cell, c));
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t h = wrap_rows<false>(corner_hash<D>(cell, c), lv);
+      scatter_row<F>(tbl + static_cast<size_t>(h) * F, g, corner_weight<D>(cell, c));
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) hashgrid_corners_kernel(const float* __restrict__ x, const __grid_constant__ LevelTable T,
+                                                               int64_t n, int n_levels, uint32_t* __restrict__ hashes,
+                                                               float* __restrict__ weights) {
+  constexpr int C = 1 << D;
+  const int level = blockIdx.y;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const LevelDev& lv = T.lv[level];
+  float xv[D];
+  load_coord<D>(x, i, xv);
+  const Cell<D> cell = make_cell<D>(xv, lv);
+  const int64_t base = (i * n_levels + level) * C;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if (hashes)
+      hashes[base + c] = lv.is_pow2 ? wrap_rows<true>(corner_hash<D>(cell, c), lv) : wrap_rows<false>(corner_hash<D>(cell, c), lv);
+    if (weights) weights[base + c] = corner_weight<D>(cell, c);
+  }
+}
+
+template <int D, int F>
+int launch_fwd(const float* x, const float* tables, const LevelTable& T, int64_t n, int n_levels, float* out,
+               cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), n_levels);
+  hashgrid_fwd_kernel<D, F><<<grid, 256, 0, s>>>(x, tables, T, n, n_levels * F, out);
+  MRI_LAUNCH_OK("hashgrid_fwd_kernel");
+  return MRI_OK;
+}
+template <int D, int F>
+int launch_bwd(const float* x, const float* go, const LevelTable& T, int64_t n, int n_levels, float* gt,
+               cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), n_levels);
+  hashgrid_bwd_kernel<D, F><<<grid, 256, 0, s>>>(x, go, T, n, n_levels * F, gt);
+  MRI_LAUNCH_OK("hashgrid_bwd_kernel");
+  return MRI_OK;
+}
+
+int check_common(const void* x, int64_t n, int dim, const mri_level_t* lv, int n_levels, int n_features) {
+  if (!x || !lv) return fail(MRI_ERR_INVALID, "hashgrid: null pointer");
+  if (n < 0) return fail(MRI_ERR_INVALID, "hashgrid: negative n");
+  if (dim < 2 || dim > MRI_MAX_DIM) return fail(MRI_ERR_UNSUPPORTED, "hashgrid: dim %d not in 2..4", dim);
+  if (n_levels < 1 || n_levels > MRI_MAX_LEVELS)
+    return fail(MRI_ERR_UNSUPPORTED, "hashgrid: n_levels %d not in 1..%d", n_levels, MRI_MAX_LEVELS);
+  if (n_features != 1 && n_features != 2 && n_features != 4 && n_features != 8)
+    return fail(MRI_ERR_UNSUPPORTED, "hashgrid: n_features %d not in {1,2,4,8}", n_features);
+  const uintptr_t need = dim == 4 ? 15 : dim == 2 ? 7 : 3;  // float4 / float2 / scalar coordinate loads
+  if ((reinterpret_cast<uintptr_t>(x) & need) != 0)
+    return fail(MRI_ERR_INVALID, "hashgrid: x must be %d-byte aligned for dim=%d", static_cast<int>(need + 1), dim);
+  return MRI_OK;
+}
+
+#define MRI_DISPATCH_DF(dim, nf, CALL)                                   \
+  switch ((dim) * 16 + (nf)) {                                           \
+    case 2 * 16 + 1: return CALL(2, 1);                                  \
+    case 2 * 16 + 2: return CALL(2, 2);                                  \
+    case 2 * 16 + 4: return CALL(2, 4);                                  \
+    case 2 * 16 + 8: return CALL(2, 8);                                  \
+    case 3 * 16 + 1: return CALL(3, 1);                                  \
+    case 3 * 16 + 2: return CALL(3, 2);                                  \
+    case 3 * 16 + 4: return CALL(3, 4);                                  \
+    case 3 * 16 + 8: return CALL(3, 8);                                  \
+    case 4 * 16 + 1: return CALL(4, 1);                                  \
+    case 4 * 16 + 2: return CALL(4, 2);                                  \
+    case 4 * 16 + 4: return CALL(4, 4);                                  \
+    case 4 * 16 + 8: return CALL(4, 8);                                  \
+    default: return fail(MRI_ERR_UNSUPPORTED, "hashgrid: no kernel for dim=%d F=%d", (dim), (nf)); \
+  }
+
+}  // namespace
+
+int make_level_table(const mri_level_t* host_levels, int n_levels, int dim, LevelTable* out) {
+  memset(out, 0, sizeof(*out));
+  for (int l = 0; l < n_levels; ++l) {
+    const mri_level_t& h = host_levels[l];
+    if (h.rows == 0) return fail(MRI_ERR_INVALID, "hashgrid: level %d has 0 rows", l);
+    LevelDev& d = out->lv[l];
+    for (int a = 0; a < MRI_MAX_DIM; ++a) d.res[a] = a < dim ? h.resolution[a] : 0.0f;
+    d.rows = h.rows;
+    d.is_pow2 = (h.rows & (h.rows - 1)) == 0 ? 1u : 0u;
+    d.pow2_mask = h.rows - 1;
+    d.offset = h.offset;
+  }
+  return MRI_OK;
+}
+
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_hashgrid_forward(const float* x, int64_t n, int dim, const float* tables,
+                                    const mri_level_t* host_levels, int n_levels, int n_features, float* out,
+                                    void* stream) {
+  int st = check_common(x, n, dim, host_levels, n_levels, n_features);
+  if (st != MRI_OK) return st;
+  if (!tables || !out) return fail(MRI_ERR_INVALID, "hashgrid_forward: null tables/out");
+  if ((reinterpret_cast<uintptr_t>(tables) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(MRI_ERR_INVALID, "hashgrid_forward: tables/out must be 16-byte aligned");
+  for (int l = 0; l < n_levels; ++l)
+    if (host_levels[l].offset % (n_features >= 4 ? 4 : n_features))
+      return fail(MRI_ERR_INVALID, "hashgrid_forward: level %d offset not aligned to the feature vector", l);
+  if (n == 0) return MRI_OK;
+  LevelTable T;
+  st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(D, F) launch_fwd<D, F>(x, tables, T, n, n_levels, out, s)
+  MRI_DISPATCH_DF(dim, n_features, CALL)
+#undef CALL
+}
+
+extern "C" int mri_hashgrid_backward(const float* x, int64_t n, int dim, const float* grad_out, float* grad_tables,
+                                     const mri_level_t* host_levels, int n_levels, int n_features, void* stream) {
+  int st = check_common(x, n, dim, host_levels, n_levels, n_features);
+  if (st != MRI_OK) return st;
+  if (!grad_out || !grad_tables) return fail(MRI_ERR_INVALID, "hashgrid_backward: null grad pointer");
+  if ((reinterpret_cast<uintptr_t>(grad_tables) & 15) || (reinterpret_cast<uintptr_t>(grad_out) & 15))
+    return fail(MRI_ERR_INVALID, "hashgrid_backward: grads must be 16-byte aligned");
+  for (int l = 0; l < n_levels; ++l)
+    if (host_levels[l].offset % (n_features >= 4 ? 4 : n_features))
+      return fail(MRI_ERR_INVALID, "hashgrid_backward: level %d offset not aligned to the feature vector", l);
+  if (n == 0) return MRI_OK;
+  LevelTable T;
+  st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(D, F) launch_bwd<D, F>(x, grad_out, T, n, n_levels, grad_tables, s)
+  MRI_DISPATCH_DF(dim, n_features, CALL)
+#undef CALL
+}
+
+extern "C" int mri_hashgrid_corners(const float* x, int64_t n, int dim, const mri_level_t* host_levels, int n_levels,
+                                    uint32_t* hashes, float* weights, void* stream) {
+  int st = check_common(x, n, dim, host_levels, n_levels, 1);
+  if (st != MRI_OK) return st;
+  if (n == 0) return MRI_OK;
+  LevelTable T;
+  st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), n_levels);
+  switch (dim) {
+    case 2: hashgrid_corners_kernel<2><<<grid, 256, 0, s>>>(x, T, n, n_levels, hashes, weights); break;
+    case 3: hashgrid_corners_kernel<3><<<grid, 256, 0, s>>>(x, T, n, n_levels, hashes, weights); break;
+    default: hashgrid_corners_kernel<4><<<grid, 256, 0, s>>>(x, T, n, n_levels, hashes, weights); break;
+  }
+  MRI_LAUNCH_OK("hashgrid_corners_kernel");
+  return MRI_OK;
+}

@@ -1,0 +1,126 @@
+// MSE loss/gradient (K5) and the dense Adam step over a flat parameter arena (K6), sm_100a.
+//
+// Both are pure HBM streams: float4 loads/stores, grid sized as a multiple of the SM count,
+// grid-stride loops.  Adam moves 28 B/param (read p,g,m,v; write p,m,v) - 32 B when it also
+// clears the gradient in the same pass (saves the separate 4 B/param memset + one launch).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mri {
+namespace {
+
+struct AdamArgs {
+  float step_size;      // lr / (1 - beta1^t)
+  float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+  float beta1, beta2, one_minus_beta1, one_minus_beta2;
+  float eps, weight_decay, grad_scale;
+  int zero_grad;
+};
+
+// torch.optim.Adam single-tensor path: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1)
+__device__ __forceinline__ void adam_update(float& p, float& g, float& m, float& v, const AdamArgs& a) {
+  float gg = g * a.grad_scale;
+  if (a.weight_decay != 0.0f) gg = fmaf(a.weight_decay, p, gg);
+  m = fmaf(a.one_minus_beta1, gg - m, m);
+  v = fmaf(a.one_minus_beta2 * gg, gg, v * a.beta2);
+  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+  p = p - a.step_size * (m / denom);
+  if (a.zero_grad) g = 0.0f;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n4, int64_t n, AdamArgs a) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_update(pp.x, gg.x, mm.x, vv.x, a);
+    adam_update(pp.y, gg.y, mm.y, vv.y, a);
+    adam_update(pp.z, gg.z, mm.z, vv.z, a);
+    adam_update(pp.w, gg.w, mm.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (a.zero_grad) reinterpret_cast<float4*>(g)[i] = gg;
+  }
+  // scalar tail (count not a multiple of 4)
+  const int64_t tail = n4 * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (tail < n) adam_update(p[tail], g[tail], m[tail], v[tail], a);
+}
+
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                  int64_t n, float inv_count, float* __restrict__ grad,
+                                                  float* __restrict__ loss) {
+  float acc = 0.0f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float d = pred[i] - target[i];
+    acc = fmaf(d, d, acc);
+    if (grad) grad[i] = 2.0f * d * inv_count;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float warp_sum[8];
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = warp_sum[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffu, s, o);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, s * inv_count);
+  }
+}
+
+}  // namespace
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_mse_loss_grad(const float* pred, const float* target, int64_t count, float inv_count,
+                                 float* grad_pred, float* loss, void* stream) {
+  if (!pred || !target) return fail(MRI_ERR_INVALID, "mse: null pointer");
+  if (count < 0) return fail(MRI_ERR_INVALID, "mse: negative count");
+  if (count == 0) return MRI_OK;
+  const int64_t want = (count + 255) / 256;
+  const int grid = static_cast<int>(want < 4LL * sm_count() ? want : 4LL * sm_count());
+  mse_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(pred, target, count, inv_count, grad_pred, loss);
+  MRI_LAUNCH_OK("mse_kernel");
+  return MRI_OK;
+}
+
+extern "C" int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t step, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                             int zero_grad, void* stream) {
+  if (!p || !g || !m || !v) return fail(MRI_ERR_INVALID, "adam: null pointer");
+  if (count < 0 || step < 1) return fail(MRI_ERR_INVALID, "adam: count must be >= 0 and step >= 1");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(MRI_ERR_INVALID, "adam: arenas must be 16-byte aligned");
+  if (count == 0) return MRI_OK;
+  // bias corrections in double, like torch's python-float arithmetic
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  AdamArgs a;
+  a.step_size = static_cast<float>(lr / bc1);
+  a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  a.beta1 = static_cast<float>(beta1);
+  a.beta2 = static_cast<float>(beta2);
+  a.one_minus_beta1 = static_cast<float>(1.0 - beta1);
+  a.one_minus_beta2 = static_cast<float>(1.0 - beta2);
+  a.eps = static_cast<float>(eps);
+  a.weight_decay = static_cast<float>(weight_decay);
+  a.grad_scale = static_cast<float>(grad_scale);
+  a.zero_grad = zero_grad;
+  const int64_t n4 = count / 4;
+  int64_t want = (n4 + 255) / 256;
+  if (want < 1) want = 1;
+  const int64_t cap = 8LL * sm_count();
+  const int grid = static_cast<int>(want < cap ? want : cap);
+  adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n4, count, a);
+  MRI_LAUNCH_OK("adam_kernel");
+  return MRI_OK;
+}

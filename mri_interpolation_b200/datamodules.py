@@ -1,0 +1,168 @@
+"""Input pipeline - the reference's ``datamodules.py`` surface (MriImage / MriDataModule) with the
+data resident on the device.
+
+Mirrors: MriImage datamodules.py:123-172 (coords = linspace per axis, 'ij' meshgrid, C-order flatten;
+intensities min-max normalised, optional [-1,1] ``norm_siren``), MriDataModule :175-252 incl.
+``upsampling()``.  The reference feeds training through a per-sample ``__getitem__`` + collate
+DataLoader with os.cpu_count() workers - its real end-to-end bottleneck.  Here the
+loaders are ``DeviceBatchLoader``s: coords/pixels live in HBM once, a shuffled epoch is a device-side
+permutation, a batch is one gather - same batches-per-epoch semantics (last batch may be short).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import nifti
+from .pl_compat import pl
+
+
+def mgrid_axes(shape: Sequence[int], norm_siren: bool = False):
+    lo = -1 if norm_siren else 0
+    return [torch.linspace(lo, 1, s) for s in shape]
+
+
+def create_mgrid(shape: Sequence[int]) -> torch.Tensor:
+    """utils.py:14-23 - (*shape, D) grid of linspace(0,1,s) coordinates."""
+    return torch.stack(torch.meshgrid(*mgrid_axes(shape), indexing="ij"), dim=-1)
+
+
+class DeviceBatchLoader:
+    """Iterable of (coords, pixels) batches cut from tensors that already live on `device`.
+
+    ``shuffle=True`` draws a fresh permutation per epoch from ``generator`` (device-side randperm).
+    ``rank``/``world_size`` give each data-parallel rank a disjoint strided share of every epoch.
+    """
+
+    def __init__(self, coords: torch.Tensor, pixels: torch.Tensor, batch_size: int, shuffle: bool = False,
+                 device: Optional[torch.device] = None, seed: int = 1337, rank: int = 0, world_size: int = 1,
+                 drop_last: bool = False):
+        self.device = torch.device(device) if device is not None else coords.device
+        self.coords = coords.to(self.device)
+        self.pixels = pixels.to(self.device)
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        self.rank, self.world_size = rank, world_size
+        self.drop_last = drop_last
+        self.dataset = torch.utils.data.TensorDataset(self.coords, self.pixels)
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(seed)
+        self.epoch = 0
+
+    def _local_count(self) -> int:
+        n = self.coords.shape[0]
+        return (n - self.rank + self.world_size - 1) // self.world_size
+
+    def __len__(self) -> int:
+        n = self._local_count()
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.coords.shape[0]
+        if self.shuffle:
+            order = torch.randperm(n, device=self.device, generator=self._gen)
+            if self.world_size > 1:
+                order = order[self.rank::self.world_size]
+            for i in range(len(self)):
+                idx = order[i * self.batch_size:(i + 1) * self.batch_size]
+                yield self.coords.index_select(0, idx), self.pixels.index_select(0, idx)
+        else:
+            if self.world_size > 1:
+                raise RuntimeError("unshuffled loaders are not sharded; use sweep.dense_sweep for inference")
+            for i in range(len(self)):
+                sl = slice(i * self.batch_size, (i + 1) * self.batch_size)
+                yield self.coords[sl], self.pixels[sl]
+        self.epoch += 1
+
+
+class MriImage(Dataset):
+    """Coordinates in ``coords`` (M, D), intensities in ``pixels`` (M, 1) (datamodules.py:123-172)."""
+
+    def __init__(self, config, image_path: str = None, norm_siren: bool = False, *args, **kwargs):
+        super().__init__()
+        path = image_path if image_path else config.image_path
+        image = nifti.load(path).get_fdata(dtype=np.float32)
+        axes = mgrid_axes(image.shape, norm_siren)
+        mgrid = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1)
+        pixels = torch.FloatTensor(image).flatten()
+        if norm_siren:
+            pixels = ((pixels - torch.min(pixels)) / (torch.max(pixels) - torch.min(pixels))) * 2 - 1
+        else:
+            pixels = (pixels - torch.min(pixels)) / (torch.max(pixels) - torch.min(pixels))
+        coords = mgrid.reshape(len(pixels), config.dim_in)
+        assert len(coords) == len(pixels)
+        self.shape = tuple(image.shape)
+        self.coords = coords.contiguous()
+        self.pixels = pixels.unsqueeze(-1)
+
+    def __len__(self):
+        return len(self.pixels)
+
+    def __getitem__(self, idx):
+        return self.coords[idx], self.pixels[idx]
+
+
+class MriDataModule(pl.LightningDataModule):
+    """ONE MRI image -> coords and pixels; train/val/test all see the same data (datamodules.py:175-252)."""
+
+    def __init__(self, config=None, device=None, *args, **kwargs):
+        super().__init__()
+        self.train_ds = None
+        self.val_ds = None
+        self.test_ds = None
+        self.config = config
+        self.device = device
+
+    def _dev(self):
+        if self.device is not None:
+            return torch.device(self.device)
+        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+
+    def prepare_data(self) -> None:
+        self.dataset = MriImage(config=self.config)
+        self.train_ds = self.dataset
+        self.test_ds = self.dataset
+        self.val_ds = self.dataset
+
+    def setup(self, stage=None):
+        pass
+
+    def _loader(self, ds, shuffle):
+        rank, world = 0, 1
+        if shuffle and torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        return DeviceBatchLoader(ds.coords, ds.pixels, self.config.batch_size, shuffle=shuffle, device=self._dev(),
+                                 rank=rank, world_size=world)
+
+    def train_dataloader(self):
+        return self._loader(self.train_ds, True)
+
+    def val_dataloader(self):
+        return self._loader(self.val_ds, False)
+
+    def test_dataloader(self):
+        return self._loader(self.test_ds, False)
+
+    def upsampling(self, shape, batch_size, norm_siren: bool = False):
+        """Mock loader over a dense grid of ``shape`` (datamodules.py:229-252); for big grids prefer
+        ``mri_interpolation_b200.sweep.dense_sweep`` which never materialises the coordinates."""
+        axes = mgrid_axes(shape, norm_siren)
+        mgrid = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1)
+        fake_pix = torch.zeros(int(np.prod(shape)))
+        coords = mgrid.reshape(len(fake_pix), len(shape))
+        assert len(coords) == len(fake_pix)
+        return DeviceBatchLoader(coords.contiguous(), fake_pix.unsqueeze(-1), batch_size, shuffle=False,
+                                 device=self._dev())
+
+
+class _OutOfScopeDataModule(pl.LightningDataModule):
+    def __init__(self, *a, **k):
+        raise NotImplementedError(f"{type(self).__name__} needs data that is not part of the hot-path scope")
+
+
+class MNISTDataModule(_OutOfScopeDataModule): ...
+class MriFramesDataModule(_OutOfScopeDataModule): ...

@@ -1,0 +1,223 @@
+"""torch.autograd glue over the C ABI (include/mri_b200.h).  CUDA fp32 only, no fallback.
+
+Gradient convention ("direct accumulation"): when a parameter already owns a ``.grad`` buffer
+(always the case once the model's parameters live in a FlatArena, see optim.py) the backward
+kernels accumulate straight into it - they are ``+=`` kernels (red.global.add) anyway - and the
+autograd Function returns ``None`` for that input, so no dense (T_l, F) gradient is ever
+materialised, copied or re-added.  Otherwise a zeroed buffer is allocated, filled and returned
+like any autograd gradient.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_IDENTITY, ACT_RELU, ACT_SINE, MriB200Error
+
+_ACT_BY_NAME = {"identity": ACT_IDENTITY, "sine": ACT_SINE, "gelu": ACT_GELU, "relu": ACT_RELU}
+
+
+def activation_code(act) -> int:
+    if isinstance(act, int):
+        return act
+    return _ACT_BY_NAME[act]
+
+
+def _direct_grad(p: torch.Tensor) -> Optional[torch.Tensor]:
+    g = getattr(p, "grad", None)
+    if g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape:
+        return g
+    return None
+
+
+# ----------------------------------------------------------------------------- hash grid
+class _TableLayout:
+    """Base pointer + per-level float offsets of a list of (rows_l, F) tables living anywhere
+    in one device's memory (normally consecutive views of the FlatArena)."""
+
+    __slots__ = ("key", "base", "levels")
+
+    def __init__(self):
+        self.key = None
+        self.base = 0
+        self.levels = None
+
+    def refresh(self, tensors: Sequence[torch.Tensor], resolutions, rows):
+        ptrs = tuple(t.data_ptr() for t in tensors)
+        if ptrs == self.key:
+            return
+        base = min(ptrs)
+        offs = []
+        for p in ptrs:
+            if (p - base) % 4:
+                raise MriB200Error("hash tables must be 4-byte aligned relative to each other")
+            offs.append((p - base) // 4)
+        self.levels = _lib.make_levels(resolutions, rows, offs)
+        self.base = base
+        self.key = ptrs
+
+
+class HashGridFn(torch.autograd.Function):
+    """encoding.py:108-128,190-191 forward; autograd of :127-128 backward (tables only - the
+    reference never needs d/dx because coordinates come from a DataLoader)."""
+
+    @staticmethod
+    def forward(ctx, x, grid, *tables):
+        n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
+        x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
+        for t in tables:
+            _lib.require_cuda_f32(t, "hash table")
+            if not t.is_contiguous():
+                raise MriB200Error("hash tables must be contiguous")
+        grid._fwd_layout.refresh(tables, grid._resolutions, grid._rows)
+        out = torch.empty((x2.shape[0], n_levels * nf), device=x.device, dtype=torch.float32)
+        _lib.call("mri_hashgrid_forward", x2.data_ptr(), x2.shape[0], dim, grid._fwd_layout.base,
+                  grid._fwd_layout.levels, n_levels, nf, out.data_ptr(), _lib.stream())
+        ctx.grid = grid
+        ctx.tables = tables
+        ctx.save_for_backward(x2)
+        ctx.lead_shape = x.shape[:-1]
+        return out.reshape(*x.shape[:-1], n_levels * nf)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grid = ctx.grid
+        (x2,) = ctx.saved_tensors
+        n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
+        go = grad_out.reshape(-1, n_levels * nf).contiguous()
+        tables = ctx.tables
+        need = [t.requires_grad for t in tables]
+        if not any(need):
+            return (None, None) + (None,) * len(tables)
+        direct = [_direct_grad(t) for t in tables]
+        if all(d is not None for d in direct):
+            targets, ret = direct, (None,) * len(tables)
+        else:
+            sizes = [(t.numel() + 3) // 4 * 4 for t in tables]
+            flat = torch.zeros(sum(sizes), device=go.device, dtype=torch.float32)
+            targets, off = [], 0
+            for t, s in zip(tables, sizes):
+                targets.append(flat[off:off + t.numel()].view_as(t))
+                off += s
+            ret = tuple(targets)
+        grid._bwd_layout.refresh(targets, grid._resolutions, grid._rows)
+        _lib.call("mri_hashgrid_backward", x2.data_ptr(), x2.shape[0], dim, go.data_ptr(), grid._bwd_layout.base,
+                  grid._bwd_layout.levels, n_levels, nf, _lib.stream())
+        return (None, None) + ret
+
+
+def hashgrid_corners(x: torch.Tensor, grid) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Parity probe: (n, L, 2^D) int64 hashes and f32 weights from the CUDA kernel."""
+    x2 = _lib.require_cuda_f32(x, "x").reshape(-1, grid.dim).contiguous()
+    n, c = x2.shape[0], 1 << grid.dim
+    hashes = torch.empty((n, grid.n_levels, c), device=x.device, dtype=torch.int32)
+    weights = torch.empty((n, grid.n_levels, c), device=x.device, dtype=torch.float32)
+    levels = _lib.make_levels(grid._resolutions, grid._rows, [0] * grid.n_levels)
+    _lib.call("mri_hashgrid_corners", x2.data_ptr(), n, grid.dim, levels, grid.n_levels, hashes.data_ptr(),
+              weights.data_ptr(), _lib.stream())
+    return hashes.to(torch.int64) & 0xFFFFFFFF, weights
+
+
+# -------------------------------------------------------------------------------- dense
+class DenseFn(torch.autograd.Function):
+    """y = act(x W^T + b) - SirenLayer.forward (models.py:153-156) / decoder Linear+act."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int, w0: float):
+        _lib.require_cuda_f32(x, "dense input")
+        _lib.require_cuda_f32(weight, "dense weight")
+        m, k = weight.shape
+        x2 = x.reshape(-1, k)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        if not weight.is_contiguous():
+            raise MriB200Error("dense weight must be contiguous")
+        n = x2.shape[0]
+        y = torch.empty((n, m), device=x.device, dtype=torch.float32)
+        needs_grad = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
+        keep_pre = needs_grad and act != ACT_IDENTITY
+        pre = torch.empty_like(y) if keep_pre else None
+        _lib.call("mri_dense_forward", x2.data_ptr(), x2.stride(0), weight.data_ptr(), _lib.ptr(bias), n, k, m, act,
+                  float(w0), y.data_ptr(), _lib.ptr(pre), _lib.stream())
+        ctx.act, ctx.w0 = act, float(w0)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.save_for_backward(x2, pre)
+        ctx.x_needs_grad = x.requires_grad
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], m)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x2, pre = ctx.saved_tensors
+        weight, bias = ctx.weight, ctx.bias
+        m, k = weight.shape
+        n = x2.shape[0]
+        gy = grad_y.reshape(n, m).contiguous()
+        dpre = torch.empty_like(gy)
+        gx = torch.empty((n, k), device=gy.device, dtype=torch.float32) if ctx.x_needs_grad else None
+        gw_direct = _direct_grad(weight)
+        gw = gw_direct if gw_direct is not None else torch.zeros_like(weight)
+        gb = gb_direct = None
+        if bias is not None:
+            gb_direct = _direct_grad(bias)
+            gb = gb_direct if gb_direct is not None else torch.zeros_like(bias)
+        _lib.call("mri_dense_backward", x2.data_ptr(), x2.stride(0), weight.data_ptr(), _lib.ptr(pre), gy.data_ptr(),
+                  n, k, m, ctx.act, ctx.w0, dpre.data_ptr(), _lib.ptr(gx), gw.data_ptr(), _lib.ptr(gb), _lib.stream())
+        return (gx.reshape(ctx.x_shape) if gx is not None else None,
+                None if gw_direct is not None else gw,
+                None if (bias is None or gb_direct is not None) else gb,
+                None, None)
+
+
+def dense(x, weight, bias=None, act="identity", w0: float = 1.0):
+    return DenseFn.apply(x, weight, bias, activation_code(act), float(w0))
+
+
+# ---------------------------------------------------------------------------------- loss
+class MseFn(torch.autograd.Function):
+    """F.mse_loss(y, y_pred) (models.py:64) with the gradient produced in the same pass.
+    ``inv_count`` defaults to 1/numel; data-parallel training passes 1/(global numel)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, inv_count: Optional[float]):
+        _lib.require_cuda_f32(pred, "prediction")
+        _lib.require_cuda_f32(target, "target")
+        if pred.shape != target.shape:
+            raise MriB200Error(f"mse_loss: shapes differ {tuple(pred.shape)} vs {tuple(target.shape)}")
+        p, t = pred.contiguous(), target.contiguous()
+        inv = float(inv_count) if inv_count is not None else 1.0 / max(p.numel(), 1)
+        loss = torch.zeros((), device=p.device, dtype=torch.float32)
+        grad = torch.empty_like(p) if pred.requires_grad else None
+        _lib.call("mri_mse_loss_grad", p.data_ptr(), t.data_ptr(), p.numel(), inv, _lib.ptr(grad), loss.data_ptr(),
+                  _lib.stream())
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None, None
+        return grad * g, None, None
+
+
+def mse_loss(a: torch.Tensor, b: torch.Tensor, inv_count: Optional[float] = None) -> torch.Tensor:
+    """Drop-in for ``F.mse_loss(y, y_pred)`` as BaseMLP.training_step calls it (target first)."""
+    if b.requires_grad or not a.requires_grad:
+        return MseFn.apply(b, a, inv_count)
+    return MseFn.apply(a, b, inv_count)
+
+
+# --------------------------------------------------------------------------------- sweep
+def grid_coords(axes: Sequence[torch.Tensor], first: int, count: int, device) -> torch.Tensor:
+    """Coordinates of voxels [first, first+count) of the C-order grid spanned by ``axes``."""
+    shape = [int(a.numel()) for a in axes]
+    flat_axes = torch.cat([a.reshape(-1).to(torch.float32) for a in axes]).to(device)
+    out = torch.empty((count, len(shape)), device=device, dtype=torch.float32)
+    import ctypes
+    cshape = (ctypes.c_int32 * len(shape))(*shape)
+    _lib.call("mri_grid_coords", flat_axes.data_ptr(), cshape, len(shape), int(first), int(count), out.data_ptr(),
+              _lib.stream())
+    return out

@@ -1,0 +1,359 @@
+"""Coordinate-network models - the reference's ``models.py`` class surface on the B200 kernels.
+
+Mirrors (reference file:line):
+  BaseMLP      models.py:20-95    Lightning glue: training_step (MSE), configure_optimizers (Adam), predict_step
+  Sine         models.py:108-114
+  SirenLayer   models.py:117-156  init U(+-1/dim_in) (first) or U(+-sqrt(sigma/dim_in)/w0), weight then bias
+  SirenNet     models.py:160-233  n_layers sine layers + identity-activated last layer (no w0 on the last)
+  HashMLP      models.py:658-754  hash-grid encoder + [Linear -> (BatchNorm1d) -> GELU -> Dropout] blocks;
+                                  forward = encoder then block-by-block loop (nb cell 37,
+                                  legacy_code/hash_experimentation.py:237-241; the shipped forward calls a
+                                  ModuleList and cannot run)
+
+Constructors consume the torch RNG in the reference's order, so ``torch.manual_seed(1337)`` gives the
+same initial state_dict (same keys, shapes and values) as the reference.  All compute runs through
+the C ABI (csrc/*.cu); inputs/parameters must be CUDA fp32 - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import encoding
+from . import functional as Fn
+from ._lib import ACT_GELU, ACT_IDENTITY, ACT_RELU, ACT_SINE
+from .optim import FusedAdam
+from .pl_compat import pl
+
+
+def _fusable_activation(mod) -> Any:
+    """Activation code if `mod` is an activation the dense kernel fuses, else None."""
+    if isinstance(mod, nn.Identity):
+        return ACT_IDENTITY
+    if isinstance(mod, nn.ReLU):
+        return ACT_RELU
+    if isinstance(mod, nn.GELU) and getattr(mod, "approximate", "none") == "none":
+        return ACT_GELU
+    return None
+
+
+class BaseMLP(pl.LightningModule):
+    """Fully connected network, base class of the other models (models.py:20-95)."""
+
+    def __init__(
+        self,
+        dim_in: int = 2,
+        dim_out: int = 1,
+        dim_hidden: int = 128,
+        n_layers: int = 8,
+        activation: torch.nn = nn.ReLU,
+        criterion: F = Fn.mse_loss,
+        lr: float = 1e-4,
+        *args,
+        **kwargs,
+    ) -> None:
+        super().__init__()
+        self.dim_in = dim_in
+        self.dim_hidden = dim_hidden
+        self.dim_out = dim_out
+        self.n_layers = n_layers
+        self.activation = activation
+        self.criterion = criterion
+        self.lr = lr
+
+        layers = []
+        for i in range(n_layers):
+            layers.append(
+                nn.Linear(
+                    in_features=dim_in if i == 0 else dim_hidden,
+                    out_features=dim_out if i == (n_layers - 1) else dim_hidden,
+                )
+            )
+            layers.append(activation())
+        self.layers = torch.nn.Sequential(*layers)
+
+    def forward(self, x) -> Any:
+        # the reference's BaseMLP.forward recurses forever (models.py:58-59); intended: the layer stack
+        mods = list(self.layers)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                act = _fusable_activation(mods[i + 1]) if i + 1 < len(mods) else None
+                if act is not None:
+                    x = Fn.dense(x, m.weight, m.bias, act)
+                    i += 2
+                    continue
+                x = Fn.dense(x, m.weight, m.bias, ACT_IDENTITY)
+            else:
+                x = m(x)
+            i += 1
+        return x
+
+    def training_step(self, batch, batch_idx) -> torch.FloatTensor:
+        x, y = batch
+        y_pred = self.forward(x)
+        loss = self.criterion(y, y_pred)
+        self.log("train_loss", loss)
+        return loss
+
+    def configure_optimizers(self):
+        # torch.optim.Adam(self.parameters(), lr) semantics (models.py:68-70), one fused kernel
+        self.optimizer = FusedAdam(self.parameters(), lr=self.lr)
+        return self.optimizer
+
+    def predict_step(self, batch, batch_idx):
+        x, y = batch
+        return self(x)
+
+    def lr_schedulers(self):
+        self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer=self.optimizer, T_max=10)
+        return self.scheduler
+
+    def set_parameters(self, theta):
+        """Manually set parameters from a matching list (models.py:87-95; used for meta learning)."""
+        p_dict = self.state_dict()
+        for p, thet in zip(p_dict, theta):
+            p_dict[p] = thet.data
+        self.load_state_dict(p_dict)
+        self.eval()
+        self.train()
+
+
+# utils for siren
+def exists(val):
+    return val is not None
+
+
+def cast_tuple(val, repeat=1):
+    return val if isinstance(val, tuple) else ((val,) * repeat)
+
+
+class Sine(nn.Module):
+    def __init__(self, w0=30.0):
+        super().__init__()
+        self.w0 = w0
+
+    def forward(self, x):
+        return torch.sin(self.w0 * x)
+
+
+class SirenLayer(nn.Module):
+    """One SIREN layer (models.py:117-156): activation(x W^T + b), sine by default, fused in one kernel."""
+
+    def __init__(
+        self,
+        dim_in: int,
+        dim_out: int = 1,
+        w0: float = 30.0,
+        sigma: float = 6.0,
+        is_first: bool = False,
+        use_bias: bool = True,
+        activation: nn = None,
+    ):
+        super().__init__()
+        self.dim_in = dim_in
+        self.is_first = is_first
+
+        weight = torch.zeros(dim_out, dim_in)
+        bias = torch.zeros(dim_out) if use_bias else None
+        self.init_(weight, bias, sigma=sigma, w0=w0)
+
+        self.weight = nn.Parameter(weight)
+        self.bias = nn.Parameter(bias) if use_bias else None
+        self.activation = Sine(w0) if activation is None else activation
+
+    def init_(self, weight, bias, sigma, w0):
+        dim = self.dim_in
+        w_std = (1 / dim) if self.is_first else (math.sqrt(sigma / dim) / w0)
+        weight.uniform_(-w_std, w_std)
+        if exists(bias):
+            bias.uniform_(-w_std, w_std)
+
+    def forward(self, x):
+        act = self.activation
+        if isinstance(act, Sine):
+            return Fn.dense(x, self.weight, self.bias, ACT_SINE, act.w0)
+        code = _fusable_activation(act)
+        if code is not None:
+            return Fn.dense(x, self.weight, self.bias, code)
+        return act(Fn.dense(x, self.weight, self.bias, ACT_IDENTITY))
+
+
+class SirenNet(BaseMLP):
+    """SIREN (models.py:160-233): implicit representation with periodic activations.
+
+    dim_in/dim_hidden/dim_out/n_layers, w0 (hidden layers), w0_initial (first layer), sigma (init
+    spread), use_bias, final_activation (None = identity), lr.  ``layers`` holds the sine layers,
+    ``last_layer`` the output layer, ``losses`` a free list the callers append to.
+    """
+
+    def __init__(
+        self,
+        dim_in: int = 3,
+        dim_hidden: int = 64,
+        dim_out: int = 1,
+        n_layers: int = 4,
+        w0: float = 30.0,
+        w0_initial: float = 30.0,
+        sigma: float = 6.0,
+        use_bias: bool = True,
+        final_activation: nn = None,
+        lr: float = 1e-4,
+        *args,
+        **kwargs,
+    ):
+        # BaseMLP.__init__() runs with its defaults first (models.py:192) and draws its 8 Linear
+        # layers from the RNG; they are then replaced by the SIREN layers, as in the reference.
+        super().__init__()
+        self.n_layers = n_layers
+        self.dim_hidden = dim_hidden
+        self.sigma = sigma
+        self.losses = []
+        self.lr = lr
+
+        self.layers = nn.ModuleList([])
+        for ind in range(n_layers):
+            is_first = ind == 0
+            layer_w0 = w0_initial if is_first else w0
+            layer_dim_in = dim_in if is_first else dim_hidden
+            self.layers.append(
+                SirenLayer(dim_in=layer_dim_in, dim_out=dim_hidden, w0=layer_w0, sigma=self.sigma,
+                           use_bias=use_bias, is_first=is_first)
+            )
+
+        final_activation = nn.Identity() if not exists(final_activation) else final_activation
+        self.last_layer = SirenLayer(dim_in=dim_hidden, dim_out=dim_out, w0=w0, sigma=self.sigma,
+                                     use_bias=use_bias, activation=final_activation)
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = layer(x)
+        return self.last_layer(x)
+
+
+class HashMLP(BaseMLP):
+    """Hash-grid encoder + small MLP decoder (models.py:658-754).
+
+    ``base_resolution`` int -> ``MultiResHashGrid``; sequence -> ``MultiResHashGridV2`` (:691-708).
+    ``batch_norm=True`` reproduces the shipped decoder blocks Linear -> BatchNorm1d -> activation ->
+    Dropout (:718-739); ``batch_norm=False`` is the notebook's Linear -> activation variant (nb cell 37).
+    ``n_layers`` reaches BaseMLP through **kwargs exactly like the reference (default 8).
+    """
+
+    def __init__(self,
+                 dim_in: int,
+                 n_levels: int,
+                 n_features_per_level: int,
+                 log2_hashmap_size: int,
+                 base_resolution: Tuple[int, ...],
+                 finest_resolution: Tuple[int, ...],
+                 interplation_method: str = 'linear',
+                 dim_hidden: int = 64,
+                 dim_out: int = 1,
+                 activation: nn = nn.GELU,
+                 dropout: float = 0.0,
+                 lr: float = 1e-4,
+                 *args,
+                 batch_norm: bool = True,
+                 **kwargs):
+        super().__init__(*args, **kwargs)
+        self.dim_in = dim_in
+        self.n_levels = n_levels
+        self.n_features_per_level = n_features_per_level
+        self.log2_hashmap_size = log2_hashmap_size
+        self.base_resolution = base_resolution
+        self.finest_resolution = finest_resolution
+        self.interpolation_method = interplation_method
+        self.dim_hidden = dim_hidden
+        self.dim_out = dim_out
+        self.dropout = dropout
+        self.lr = lr
+        self.batch_norm = batch_norm
+        self.latents = []  # encoder outputs kept by predict_step for visualisation (:689,749)
+        self.keep_latents = True
+
+        if isinstance(self.base_resolution, int):
+            self.encoder = encoding.MultiResHashGrid(
+                dim=self.dim_in, n_levels=self.n_levels, n_features_per_level=self.n_features_per_level,
+                log2_hashmap_size=self.log2_hashmap_size, base_resolution=self.base_resolution,
+                finest_resolution=self.finest_resolution)
+        else:
+            self.encoder = encoding.MultiResHashGridV2(
+                dim=self.dim_in, n_levels=self.n_levels, n_features_per_level=self.n_features_per_level,
+                log2_hashmap_size=self.log2_hashmap_size, base_resolution=self.base_resolution,
+                finest_resolution=self.finest_resolution)
+
+        self.encoding_dim_out = self.n_levels * self.n_features_per_level
+
+        self.decoder = torch.nn.ModuleList()
+        for i in range(self.n_layers):
+            in_features = self.encoding_dim_out if i == 0 else self.dim_hidden
+            out_features = self.dim_out if i == (self.n_layers - 1) else self.dim_hidden
+            mods = [torch.nn.Linear(in_features=in_features, out_features=out_features)]
+            if batch_norm:
+                mods.append(torch.nn.BatchNorm1d(num_features=out_features))
+            mods.append(activation())
+            if batch_norm:
+                mods.append(torch.nn.Dropout(p=dropout, inplace=False))
+            self.decoder.append(torch.nn.Sequential(*mods))
+
+    @staticmethod
+    def _run_block(block, x):
+        mods = list(block)
+        lin = mods[0]
+        rest = mods[1:]
+        if len(rest) >= 1:
+            act = _fusable_activation(rest[0])
+            tail_inert = all(isinstance(m, nn.Dropout) and (m.p == 0.0 or not m.training) for m in rest[1:])
+            if act is not None and tail_inert:
+                return Fn.dense(x, lin.weight, lin.bias, act)
+        x = Fn.dense(x, lin.weight, lin.bias, ACT_IDENTITY)
+        for m in rest:  # BatchNorm1d & co: batch statistics need a second pass
+            x = m(x)
+        return x
+
+    def decode(self, z):
+        for block in self.decoder:
+            z = self._run_block(block, z)
+        return z
+
+    def forward(self, x):
+        return self.decode(self.encoder(x))
+
+    def predict_step(self, batch, batch_idx):
+        x, y = batch
+        z = self.encoder(x)
+        if self.keep_latents:
+            self.latents.append(z)
+        return self.decode(z)
+
+    def get_latents(self):
+        return self.latents
+
+
+class _OutOfScope(pl.LightningModule):
+    """Reference model-zoo variants that are not on the north-star hot path: the
+    names stay importable because config/base.py imports them, but they are not implemented."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"{type(self).__name__} is outside the B200 hot-path scope (SIREN, hash-grid + MLP, dense sweep, "
+            f"Adam); see DESIGN.md 'Out of scope'")
+
+
+class Modulator(_OutOfScope): ...
+class ModulatedSirenNet(_OutOfScope): ...
+class HashSirenNet(_OutOfScope): ...
+class PsfSirenNet(_OutOfScope): ...
+class RffNet(_OutOfScope): ...
+class TcnnHashMLP(_OutOfScope): ...
+class RealGaborLayer(_OutOfScope): ...
+class ComplexGaborLayer(_OutOfScope): ...
+class GaborNet(_OutOfScope): ...
+class MultiSiren(_OutOfScope): ...
+class MultiHashMLP(_OutOfScope): ...

@@ -1,0 +1,156 @@
+"""Flat parameter arena + fused dense Adam (K6) with the data-parallel gradient all-reduce.
+
+Reference: ``BaseMLP.configure_optimizers`` returns ``torch.optim.Adam(self.parameters(), lr)``
+(models.py:68-70) - dense Adam, defaults beta=(0.9, 0.999), eps=1e-8, no weight decay; every
+table row's m/v decay every step even with a zero gradient.  ``FusedAdam`` keeps those semantics
+but runs ONE kernel over one flat buffer [tables | MLP] (28 B/param, 32 B with the fused
+gradient clear), and - when torch.distributed is initialised with world_size > 1 - sums the flat
+gradient over the ranks with a single NCCL all-reduce (NVLink 5 / NVSwitch) right before it.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import MriB200Error
+from .distributed import allreduce_sum_
+
+_ALIGN = 4  # floats: every parameter starts 16-byte aligned inside the arena
+
+
+class FlatArena:
+    """Re-homes a list of parameters into one flat fp32 buffer (and their gradients into another),
+    keeping every ``nn.Parameter`` object - hence every state_dict key and shape - unchanged."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        if not self.params:
+            raise MriB200Error("FlatArena: no parameters")
+        dev = self.params[0].device
+        for p in self.params:
+            if p.device != dev:
+                raise MriB200Error("FlatArena: parameters live on different devices")
+            if not p.is_cuda or p.dtype != torch.float32:
+                raise MriB200Error(
+                    f"FlatArena: parameters must be CUDA float32 (got {p.device}, {p.dtype}); move the model to "
+                    f"the GPU before configure_optimizers() - there is no CPU fallback")
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = total
+        self.data = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.data[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                old_grad = p.grad
+                p.data = view
+                gview = self.grad[off:off + p.numel()].view(p.shape)
+                if old_grad is not None:
+                    gview.copy_(old_grad)
+                p.grad = gview
+
+    def intact(self) -> bool:
+        """True while every parameter (and its .grad) still aliases the arena (``model.to()`` or
+        ``zero_grad(set_to_none=True)`` would break that)."""
+        base, gbase = self.data.data_ptr(), self.grad.data_ptr()
+        for p, off in zip(self.params, self.offsets):
+            if p.data_ptr() != base + 4 * off or p.grad is None or p.grad.data_ptr() != gbase + 4 * off:
+                return False
+        return True
+
+    def reattach_grads(self) -> None:
+        for p, off in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                gview = self.grad[off:off + p.numel()].view(p.shape)
+                if p.grad is not None:
+                    gview.copy_(p.grad)
+                else:
+                    gview.zero_()
+                p.grad = gview
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """Dense Adam with torch.optim.Adam's semantics, one kernel over a FlatArena.
+
+    ``process_group``: None -> the default group when torch.distributed is initialised.
+    ``grad_average``: gradients are summed over ranks and scaled by 1/world_size (each rank computes
+    the mean loss of its own shard of the global batch), i.e. the update equals the single-GPU
+    update on the concatenated batch up to fp32 summation order.
+    """
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 process_group=None, grad_average: bool = True, fuse_zero_grad: bool = True):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise MriB200Error("FusedAdam handles a single parameter group (the reference uses one)")
+        plist = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        self.arena = FlatArena(plist)
+        self.exp_avg = torch.zeros_like(self.arena.data)
+        self.exp_avg_sq = torch.zeros_like(self.arena.data)
+        self.step_count = 0
+        self.process_group = process_group
+        self.grad_average = grad_average
+        self.fuse_zero_grad = fuse_zero_grad
+        self._grads_clean = True  # freshly allocated arena gradient is zero
+        self.allreduce_count = 0
+
+    # -- distributed
+    def _world(self) -> int:
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group)
+        return 1
+
+    def sync_gradients(self) -> float:
+        """Sum the flat gradient over the data-parallel ranks; returns the scale Adam must apply."""
+        if self._world() == 1:
+            return 1.0
+        inv_world = allreduce_sum_(self.arena.grad, self.process_group)
+        self.allreduce_count += 1
+        return inv_world if self.grad_average else 1.0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if not self.arena.intact():
+            self.arena.reattach_grads()
+            if not self.arena.intact():
+                raise MriB200Error("FusedAdam: parameters no longer alias the flat arena (was the model moved "
+                                   "after configure_optimizers()?)")
+        scale = self.sync_gradients()
+        g = self.param_groups[0]
+        self.step_count += 1
+        _lib.call("mri_adam_step", self.arena.data.data_ptr(), self.arena.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self.arena.numel, self.step_count, float(g["lr"]), float(g["betas"][0]),
+                  float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(scale),
+                  1 if self.fuse_zero_grad else 0, _lib.stream())
+        self._grads_clean = bool(self.fuse_zero_grad)
+        return loss
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Gradients stay views of the arena.  The first zero_grad() after a fused step is free (the
+        Adam kernel already cleared them); any other call clears the arena."""
+        if not self._grads_clean:
+            self.arena.grad.zero_()
+        self.arena.reattach_grads()
+        self._grads_clean = False
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "param_groups": [{k: v for k, v in self.param_groups[0].items() if k != "params"}]}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        for k, v in sd["param_groups"][0].items():
+            self.param_groups[0][k] = v

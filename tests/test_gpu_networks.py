@@ -1,0 +1,196 @@
+"""GPU parity: dense/SIREN/decoder kernels, MSE, Adam and whole-model training steps against the
+oracle (torch fp32 on CPU) and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import SIREN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+ACTS = {"identity": lambda p, w0: p, "sine": lambda p, w0: torch.sin(w0 * p), "gelu": lambda p, w0: F.gelu(p),
+        "relu": lambda p, w0: F.relu(p)}
+
+
+@pytest.mark.parametrize("n,k,m", [(300, 3, 64), (1000, 64, 1), (257, 32, 64), (129, 4, 256), (513, 256, 256),
+                                   (64, 48, 3), (1, 5, 7), (2050, 352, 352), (77, 64, 16), (90, 17, 33)])
+@pytest.mark.parametrize("act", ["identity", "sine", "gelu", "relu"])
+def test_dense_forward_backward_vs_torch(n, k, m, act):
+    from mri_interpolation_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(n * 7 + k * 3 + m)
+    x = (torch.rand(n, k, generator=gen) * 2 - 1).requires_grad_()
+    w = ((torch.rand(m, k, generator=gen) * 2 - 1) / k ** 0.5).requires_grad_()
+    b = ((torch.rand(m, generator=gen) * 2 - 1) * 0.1).requires_grad_()
+    w0 = 30.0 if act == "sine" else 1.0
+    y_ref = ACTS[act](F.linear(x, w, b), w0)
+    gy = torch.randn(n, m, generator=gen)
+    y_ref.backward(gy)
+    xd, wd, bd = (t.detach().to(DEV).requires_grad_() for t in (x, w, b))
+    y = Fn.dense(xd, wd, bd, act, w0)
+    tol = 2e-4 if act == "sine" else 1e-5  # sin(30 * pre): argument rounding is amplified by w0
+    assert rel_err(y, y_ref) < tol
+    y.backward(gy.to(DEV))
+    assert rel_err(xd.grad, x.grad) < max(tol, 1e-4)
+    assert rel_err(wd.grad, w.grad) < max(tol, 1e-4)
+    assert rel_err(bd.grad, b.grad) < max(tol, 1e-4)
+
+
+def test_dense_no_bias_and_strided_input():
+    from mri_interpolation_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(1)
+    big = torch.rand(200, 40, generator=gen)
+    w = torch.rand(24, 32, generator=gen) - 0.5
+    x = big[:, 4:36]  # row stride 40
+    ref = F.gelu(F.linear(x, w))
+    out = Fn.dense(big.to(DEV)[:, 4:36], w.to(DEV), None, "gelu")
+    assert rel_err(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", SIREN_CASES)
+def test_sirennet_matches_reference_vectors(case):
+    from mri_interpolation_b200 import models
+    fx = load_golden(f"siren_{case}.npz")
+    kw = {k[3:]: fx[k].item() for k in fx if k.startswith("kw_")}
+    torch.manual_seed(1337)
+    net = models.SirenNet(**kw).to(DEV)
+    x, y = torch.from_numpy(fx["x"]).to(DEV), torch.from_numpy(fx["y"]).to(DEV)
+    pred = net(x)
+    torch.testing.assert_close(pred.cpu(), torch.from_numpy(fx["pred"]), rtol=RTOL, atol=2e-5)
+    loss = net.training_step((x, y), 0)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-5
+    loss.backward()
+    for name, p in net.named_parameters():
+        if f"grad:{name}" in fx:
+            assert rel_err(p.grad, torch.from_numpy(fx[f"grad:{name}"])) < RTOL, name
+
+
+def test_hashmlp_notebook_variant_matches_reference_vectors():
+    from mri_interpolation_b200 import models
+    fx = load_golden("hashmlp_small.npz")
+    kw = {k[3:]: fx[k].item() for k in fx if k.startswith("kw_")}
+    net = models.HashMLP(**kw, batch_norm=False)
+    net.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith("param:")}, strict=False)
+    net = net.to(DEV)
+    x, y = torch.from_numpy(fx["x"]).to(DEV), torch.from_numpy(fx["y"]).to(DEV)
+    pred = net(x)
+    torch.testing.assert_close(pred.cpu(), torch.from_numpy(fx["pred"]), rtol=RTOL, atol=1e-6)
+    loss = net.training_step((x, y), 0)
+    assert abs(float(loss) - float(fx["loss"])) < 1e-6
+    loss.backward()
+    for name, p in net.named_parameters():
+        if f"grad:{name}" in fx and not name.startswith("layers."):
+            assert rel_err(p.grad, torch.from_numpy(fx[f"grad:{name}"])) < RTOL, name
+    # predict_step keeps the latents like the reference (models.py:746-751)
+    out = net.predict_step((x, y), 0)
+    assert torch.equal(out, pred.detach()) and len(net.get_latents()) == 1
+    torch.testing.assert_close(net.get_latents()[0].cpu(), torch.from_numpy(fx["latents"]), rtol=RTOL, atol=1e-6)
+
+
+def test_hashmlp_batchnorm_variant_matches_reference_vectors():
+    from mri_interpolation_b200 import models
+    fx = load_golden("hashmlp_bn_small.npz")
+    kw = {k[3:]: fx[k].item() for k in fx if k.startswith("kw_")}
+    net = models.HashMLP(**kw)  # shipped decoder: Linear -> BatchNorm1d -> GELU -> Dropout
+    net.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith("param:")}, strict=False)
+    net = net.to(DEV).train()
+    x, y = torch.from_numpy(fx["x"]).to(DEV), torch.from_numpy(fx["y"]).to(DEV)
+    pred = net(x)
+    torch.testing.assert_close(pred.cpu(), torch.from_numpy(fx["pred"]), rtol=RTOL, atol=1e-5)
+    net.training_step((x, y), 0).backward()
+    for name, p in net.named_parameters():
+        if f"grad:{name}" in fx and not name.startswith("layers."):
+            assert rel_err(p.grad, torch.from_numpy(fx[f"grad:{name}"])) < 5e-3, name
+    for k, v in fx.items():
+        if k.startswith("buffer:") and "running" in k:
+            torch.testing.assert_close(dict(net.named_buffers())[k[7:]].cpu(), torch.from_numpy(v), rtol=1e-4, atol=1e-6)
+
+
+def test_mse_loss_and_grad():
+    from mri_interpolation_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(2)
+    for shape in [(1, 1), (1000, 1), (333, 3), (70001, 1)]:
+        y = torch.rand(shape, generator=gen)
+        p = torch.rand(shape, generator=gen).requires_grad_()
+        ref = F.mse_loss(y, p)
+        ref.backward()
+        pd = p.detach().to(DEV).requires_grad_()
+        loss = Fn.mse_loss(y.to(DEV), pd)
+        assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, float(ref))
+        loss.backward()
+        assert rel_err(pd.grad, p.grad) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["default", "tcnn_like", "l2"])
+def test_fused_adam_matches_torch_trajectory(name):
+    from mri_interpolation_b200.optim import FusedAdam
+    fx = load_golden(f"adam_{name}.npz")
+    p = torch.nn.Parameter(torch.from_numpy(fx["p0"]).to(DEV))
+    opt = FusedAdam([p], lr=float(fx["lr"]), betas=(float(fx["beta1"]), float(fx["beta2"])), eps=float(fx["eps"]),
+                    weight_decay=float(fx["weight_decay"]))
+    for step, g in enumerate(fx["grads"]):
+        p.grad.copy_(torch.from_numpy(g))
+        opt.step()
+        np.testing.assert_allclose(p.detach().cpu().numpy(), fx["params"][step], rtol=2e-6, atol=1e-9)
+        assert float(p.grad.abs().max()) == 0.0  # gradient cleared in the same pass
+        opt.zero_grad()
+
+
+def test_fused_adam_odd_sizes_and_arena_views():
+    from mri_interpolation_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in [(3,), (5, 7), (1,), (1026,)]]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ps]
+    opt = FusedAdam(ps, lr=1e-2)
+    ropt = torch.optim.Adam(ref, lr=1e-2)
+    assert all(p.data_ptr() >= opt.arena.data.data_ptr() for p in ps)
+    for _ in range(3):
+        for p, r in zip(ps, ref):
+            g = torch.randn(r.shape)
+            r.grad = g.clone()
+            p.grad.copy_(g)
+        opt.step()
+        ropt.step()
+    for p, r in zip(ps, ref):
+        torch.testing.assert_close(p.detach().cpu(), r.detach(), rtol=2e-6, atol=1e-8)
+
+
+def test_training_steps_track_the_oracle():
+    """5 full steps (hash grid + decoder + MSE + Adam) from identical init and batches: parameters stay
+    within summation-order noise of the oracle's torch.optim.Adam run."""
+    from mri_interpolation_b200 import models
+    from oracle import hashgrid, networks
+    kw = dict(dim_in=3, n_levels=6, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4,
+              finest_resolution=64, dim_hidden=32, dim_out=1, n_layers=2)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, lr=5e-3)
+    torch.manual_seed(1337)
+    params, levels = networks.hashmlp_init(**kw)
+    ref = {k: v.clone().requires_grad_() for k, v in params.items() if not k.startswith("layers.")}
+    ropt = torch.optim.Adam(list(ref.values()), lr=5e-3)
+    net = net.to(DEV)
+    opt = net.configure_optimizers()
+    gen = torch.Generator().manual_seed(3)
+    for step in range(5):
+        x, y = torch.rand(2000, 3, generator=gen), torch.rand(2000, 1, generator=gen)
+        ropt.zero_grad()
+        lr_ = F.mse_loss(y, networks.hashmlp_forward(x, ref, levels, 2, False))
+        lr_.backward()
+        ropt.step()
+        opt.zero_grad()
+        loss = net.training_step((x.to(DEV), y.to(DEV)), step)
+        loss.backward()
+        opt.step()
+        assert abs(float(loss) - float(lr_)) < 1e-5
+    sd = net.state_dict()
+    for k, v in ref.items():
+        assert rel_err(sd[k], v.detach()) < 1e-4, k

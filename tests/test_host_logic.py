@@ -1,0 +1,226 @@
+"""CPU: host-side logic of the product package - construction parity with the reference (seeded
+state_dicts bit-identical to the golden fixtures), level geometry, NIfTI reader, loaders, the
+Lightning stand-in's orchestration, slab/batch partitioning."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+from conftest import SAMPLE, SIREN_CASES, load_golden
+from mri_interpolation_b200 import config, datamodules, distributed, encoding, metrics, models, nifti, sweep
+from mri_interpolation_b200.pl_compat import pl
+
+
+@pytest.mark.parametrize("case", SIREN_CASES)
+def test_sirennet_seeded_state_dict_equals_reference(case):
+    fx = load_golden(f"siren_{case}.npz")
+    kw = {k[3:]: fx[k].item() for k in fx if k.startswith("kw_")}
+    torch.manual_seed(1337)
+    net = models.SirenNet(**kw)
+    sd = net.state_dict()
+    ref_keys = {k[6:] for k in fx if k.startswith("param:")}
+    assert set(sd.keys()) == ref_keys
+    for k in ref_keys:
+        assert np.array_equal(sd[k].numpy(), fx[f"param:{k}"]), k
+
+
+def test_siren_param_counts_known_answers():
+    assert sum(p.numel() for p in models.SirenNet(dim_in=2, dim_hidden=352, n_layers=4).parameters()) == 374177  # nb:825
+    assert sum(p.numel() for p in models.SirenNet(dim_in=3, dim_hidden=1408, n_layers=4).parameters()) == 5958657  # nb:1347
+    assert sum(p.numel() for p in models.SirenNet(dim_in=3, dim_hidden=1024, n_layers=8).parameters()) == 7352321
+    assert sum(p.numel() for p in models.SirenNet(dim_in=4, dim_hidden=256, n_layers=5).parameters()) == 264705
+
+
+def test_hashmlp_seeded_state_dict_equals_reference():
+    fx = load_golden("hashmlp_small.npz")
+    kw = {k[3:]: fx[k].item() for k in fx if k.startswith("kw_")}
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw)
+    sd = net.state_dict()
+    for k in fx:
+        if k.startswith("param:") and "embedding" not in k:
+            assert np.array_equal(sd[k[6:]].numpy(), fx[k]), k
+    # same keys as the reference's HashMLP incl. BatchNorm buffers and the dead BaseMLP stack
+    fb = load_golden("hashmlp_bn_small.npz")
+    ref_keys = {k.split(":", 1)[1] for k in fb if k.startswith(("param:", "buffer:"))}
+    assert set(sd.keys()) == ref_keys
+    # embeddings: U(-1e-4, 1e-4) after the N(0,1) draw
+    w = sd["encoder.levels.0.embedding.weight"]
+    assert float(w.abs().max()) <= 1e-4
+
+
+def test_notebook_variant_has_no_batchnorm():
+    net = models.HashMLP(dim_in=3, n_levels=2, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4,
+                         finest_resolution=8, dim_hidden=16, n_layers=2, batch_norm=False)
+    assert [type(m).__name__ for m in net.decoder[0]] == ["Linear", "GELU"]
+    assert net.decoder[1][0].out_features == 1
+
+
+def test_encoder_geometry_matches_reference():
+    g = load_golden("geometry.npz")
+    enc = encoding.MultiResHashGrid(dim=4, **config.g4_hash_kwargs())
+    assert [lv.resolution for lv in enc.levels] == g["g4_res"].tolist()
+    assert [lv.hashmap_size for lv in enc.levels] == g["g4_rows"].tolist()
+    assert enc.output_dim == 32 and enc.input_dim == 4
+    assert sum(p.numel() for p in enc.parameters()) == 15279648
+    v2 = encoding.MultiResHashGridV2(dim=3, n_levels=8, n_features_per_level=2, log2_hashmap_size=23,
+                                     base_resolution=(64, 64, 5), finest_resolution=(512, 512, 15))
+    assert sum(p.numel() for p in v2.parameters()) == 6009032  # nb:2792
+    assert np.array_equal(np.asarray([lv.resolution.tolist() for lv in v2.levels]), g["nbv2_res"].astype(float))
+    assert list(v2.state_dict().keys())[0] == "levels.0.embedding.weight"
+
+
+def test_shipped_hashconfig_tuple_mismatch_fails_at_forward_like_reference():
+    # config/base.py:73-74 ships 3-tuples with dim_in=4: the reference constructs, then fails in forward
+    enc = encoding.MultiResHashGridV2(dim=4, n_levels=2, n_features_per_level=1, log2_hashmap_size=10,
+                                      base_resolution=(64, 64, 5), finest_resolution=(352, 352, 15))
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(3, 4))
+
+
+def test_fast_hash_utility_matches_oracle():
+    from oracle import hashgrid
+    gen = torch.Generator().manual_seed(3)
+    ind = torch.randint(0, 3000, (50, 16, 4), generator=gen)
+    a = encoding.fast_hash(ind.clone(), torch.tensor(encoding.PRIMES), 65536)
+    assert torch.equal(a, hashgrid.spatial_hash(ind, 65536))
+
+
+def test_out_of_scope_names_importable_but_not_constructible():
+    for name in ("HashSirenNet", "ModulatedSirenNet", "MultiHashMLP", "MultiSiren", "RffNet", "GaborNet"):
+        with pytest.raises(NotImplementedError):
+            getattr(models, name)()
+
+
+def test_nifti_reader_sample_volume_facts():
+    img = nifti.load(SAMPLE)
+    assert img.shape == (352, 352, 6, 15) and img.raw.dtype == np.int16
+    assert img.slope == pytest.approx(27.2891, abs=1e-4) and img.inter == 0.0
+    assert int(img.raw.max()) == 91 and np.unique(img.raw).size == 92
+    assert (img.raw != 0).mean() == pytest.approx(0.479, abs=1e-3)
+    data = img.get_fdata(np.float32)
+    assert data.dtype == np.float32 and np.array_equal(data, img.raw.astype(np.float32) * np.float32(img.slope))
+
+
+def test_nifti_roundtrip(tmp_path):
+    a = np.random.default_rng(0).random((5, 4, 3, 2)).astype(np.float32)
+    for name in ("a.nii", "a.nii.gz"):
+        nifti.save(a, str(tmp_path / name))
+        b = nifti.load(str(tmp_path / name))
+        assert b.shape == a.shape and np.array_equal(b.get_fdata(np.float32), a)
+
+
+def test_mriimage_matches_reference_recipe():
+    cfg = config.HashConfig()
+    ds = datamodules.MriImage(cfg)
+    assert ds.coords.shape == (11151360, 4) and ds.pixels.shape == (11151360, 1)
+    # C-order flatten: last axis (time) fastest; first step on the time axis = 1/14
+    assert torch.equal(ds.coords[0], torch.zeros(4)) and float(ds.coords[1, 3]) == pytest.approx(1 / 14)
+    assert float(ds.coords[15, 2]) == pytest.approx(1 / 5)
+    assert float(ds.pixels.min()) == 0.0 and float(ds.pixels.max()) == 1.0
+    raw = nifti.load(cfg.image_path).raw.reshape(-1)
+    np.testing.assert_allclose(ds.pixels[:, 0].numpy(), raw / 91.0, rtol=0, atol=1e-7)
+    x, y = ds[123456]
+    assert x.shape == (4,) and y.shape == (1,)
+
+
+def test_device_batch_loader_epoch_semantics():
+    coords = torch.arange(103, dtype=torch.float32).reshape(-1, 1)
+    pix = coords.clone()
+    ld = datamodules.DeviceBatchLoader(coords, pix, 10, shuffle=True, device="cpu", seed=1)
+    assert len(ld) == 11
+    seen = torch.cat([x for x, _ in ld]).flatten()
+    assert seen.shape[0] == 103 and torch.equal(seen.sort().values, coords.flatten())
+    second = torch.cat([x for x, _ in ld]).flatten()
+    assert not torch.equal(seen, second)  # new permutation every epoch
+    plain = [x for x, _ in datamodules.DeviceBatchLoader(coords, pix, 50, device="cpu")]
+    assert [p.shape[0] for p in plain] == [50, 50, 3] and torch.equal(torch.cat(plain), coords)
+    # data-parallel shares are disjoint and cover the epoch
+    shards = []
+    for r in range(3):
+        ld = datamodules.DeviceBatchLoader(coords, pix, 8, shuffle=True, device="cpu", seed=5, rank=r, world_size=3)
+        shards.append(torch.cat([x for x, _ in ld]).flatten())
+    allv = torch.cat(shards)
+    assert allv.shape[0] == 103 and torch.equal(allv.sort().values, coords.flatten())
+
+
+def test_slab_and_batch_partition():
+    for total in (1, 7, 1000, 21559296):
+        for w in (1, 2, 4, 8):
+            spans = [sweep.slab_range(total, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (f0, c0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + c0 == f1
+    assert distributed.split_batch(1 << 22, 3, 8) == (3 << 19, 1 << 19)
+
+
+def test_upsampling_loader_matches_create_mgrid():
+    dm = datamodules.MriDataModule(config=None, device="cpu")
+    ld = dm.upsampling((4, 3, 5), batch_size=7)
+    coords = torch.cat([x for x, _ in ld])
+    assert torch.equal(coords, datamodules.create_mgrid((4, 3, 5)).reshape(-1, 3))
+
+
+class _ToyModule(pl.LightningModule):
+    def __init__(self):
+        super().__init__()
+        self.lin = nn.Linear(2, 1)
+        self.steps = 0
+
+    def forward(self, x):
+        return self.lin(x)
+
+    def training_step(self, batch, batch_idx):
+        x, y = batch
+        loss = nn.functional.mse_loss(self(x), y)
+        self.log("train_loss", loss)
+        self.steps += 1
+        return loss
+
+    def predict_step(self, batch, batch_idx):
+        return self(batch[0])
+
+    def configure_optimizers(self):
+        return torch.optim.SGD(self.parameters(), lr=0.1)
+
+
+def test_trainer_standin_fit_predict_logging(tmp_path):
+    torch.manual_seed(0)
+    x = torch.rand(64, 2)
+    y = (x @ torch.tensor([[2.0], [-1.0]])) + 0.5
+    loader = datamodules.DeviceBatchLoader(x, y, 16, shuffle=True, device="cpu")
+    model = _ToyModule()
+    tr = pl.Trainer(accelerator="cpu", max_epochs=30, precision=32, default_root_dir=str(tmp_path),
+                    accumulate_grad_batches=None)
+    tr.fit(model, loader)
+    assert model.steps == 30 * 4 and tr.global_step == 120
+    start = float(nn.functional.mse_loss(_ToyModule()(x), y))
+    pred = torch.concat(tr.predict(model, datamodules.DeviceBatchLoader(x, y, 16, device="cpu")))
+    assert pred.shape == (64, 1) and float(nn.functional.mse_loss(pred, y)) < 0.2 * start
+    assert os.path.basename(model.logger.log_dir) == "version_0" and model.logger.version == 0
+    assert os.path.isfile(os.path.join(model.logger.log_dir, "metrics.csv"))
+    ck = [f for f in os.listdir(os.path.join(model.logger.log_dir, "checkpoints"))]
+    assert ck and ck[0].endswith(".ckpt")
+    again = _ToyModule.load_from_checkpoint(os.path.join(model.logger.log_dir, "checkpoints", ck[0]))
+    assert torch.equal(again.lin.weight, model.lin.weight)
+    # accumulate_grad_batches: fewer optimiser steps; dict schedule like launcher.py:159
+    m2 = _ToyModule()
+    tr2 = pl.Trainer(accelerator="cpu", max_epochs=2, precision=32, default_root_dir=str(tmp_path),
+                     accumulate_grad_batches={0: 2})
+    tr2.fit(m2, loader)
+    assert tr2.global_step == 4 and m2.logger.version == 1
+    with pytest.raises(NotImplementedError):
+        pl.Trainer(precision=16)
+
+
+def test_metrics_module():
+    rng = np.random.default_rng(0)
+    a = rng.random((16, 16, 2, 3)).astype(np.float32)
+    assert metrics.peak_signal_noise_ratio(a, a + 0.01) == pytest.approx(40.0, abs=1e-3)
+    assert metrics.structural_similarity(a, a) == pytest.approx(1.0)
+    from oracle import sweep as osweep
+    b = np.clip(a + rng.normal(0, 0.05, a.shape).astype(np.float32), 0, 1)
+    assert metrics.structural_similarity(a, b) == pytest.approx(osweep.ssim_slices(a, b), abs=1e-12)
+    assert metrics.peak_signal_noise_ratio(a, b) == pytest.approx(osweep.psnr(a, b), abs=1e-12)
