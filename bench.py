@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the coordinate-network hot path (BASELINE.json metric: training coords/s, plus inference
+voxels/s, with % of roofline and the reference's CPU path timed beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch-log2 B]
+
+Workload (configs[1] of BASELINE.json, named in `config.workload`): hash-grid encoder G4
+(config/hash_config.json: L=16, F=2, T=2^19, base 16, x1.4 -> finest 2489; 15 279 648 table params)
++ 2-layer GELU decoder (64 hidden), fitted to the sample ankle volume (352x352x6x15, x,y,z,t coords),
+fp32, Adam lr 5e-3, 2^B coordinates per step PER GPU (weak scaling; N>1 adds one NCCL all-reduce of the
+flat gradient arena per step).  One step = sample voxel indices -> synthesise coords/gather intensities
+-> hash encode -> decoder -> MSE -> backward (decoder, hash scatter) -> [all-reduce] -> fused Adam.
+
+value : device-resident inputs, CUDA-event timing, max over ranks.
+e2e   : same step through the public LightningModule API with HOST (pinned) batches: H2D copy of the
+        batch and D2H read of the loss inside the timed region.
+roofline : dominant kernel (hash-grid scatter backward) timed alone with CUDA events, L2 flushed between
+        launches; algorithmic bytes / duration against MEASURED_PEAKS.json's HBM copy bandwidth.
+cpu_baseline : the oracle port of the reference's PyTorch path on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G4 = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, finest_resolution=2489)
+SAMPLE = os.path.join(ROOT, "data", "sample_ankle_dyn_mri.nii.gz")
+SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (config 3)
+HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-log2", type=int, default=19)
+    ap.add_argument("--cpu-batch-log2", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def oracle_step_fn(batch_log2: int):
+    """One training step of the reference's PyTorch CPU path (oracle port): G4 + 2x64 GELU decoder + Adam."""
+    import torch.nn.functional as F
+    from oracle import networks, sweep as osweep
+    from mri_interpolation_b200 import nifti
+    torch.manual_seed(1337)
+    params, levels = networks.hashmlp_init(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, **G4)
+    params = {k: v.requires_grad_() for k, v in params.items() if not k.startswith("layers.")}
+    opt = torch.optim.Adam(list(params.values()), lr=5e-3)
+    vol = torch.from_numpy(nifti.load(SAMPLE).get_fdata(np.float32))
+    pixels = osweep.normalise_intensities(vol)
+    axes = [osweep.axis_values(s) for s in vol.shape]
+    shape = torch.tensor(vol.shape)
+    gen = torch.Generator().manual_seed(1337)
+    n = 1 << batch_log2
+
+    def step():
+        idx = torch.randint(0, pixels.shape[0], (n,), generator=gen)
+        rem, cols = idx.clone(), []
+        for d in range(3, -1, -1):
+            cols.append(axes[d][rem % shape[d]])
+            rem = rem // shape[d]
+        x = torch.stack(cols[::-1], dim=-1)
+        opt.zero_grad()
+        loss = F.mse_loss(pixels[idx], networks.hashmlp_forward(x, params, levels, 2, False))
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    return step, n
+
+
+def time_oracle(batch_log2: int, steps: int, warmup: int):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, n = oracle_step_fn(batch_log2)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    value, dt, n = time_oracle(args.cpu_batch_log2, steps, warm)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "sample_ankle_dyn_mri.nii.gz (bundled) + random-init weights",
+        "config": workload_config(args, cpu_sample=n),
+        "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of 2^{args.cpu_batch_log2} coords (oracle port of the reference's "
+                                   f"PyTorch CPU path: hash G4 + decoder + MSE + torch.optim.Adam)"},
+        "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, cpu_sample=None):
+    cfg = {"workload": "hash-grid G4 (L16 F2 T2^19 base16 finest2489, 15.28M table params) + 2x64 GELU decoder "
+                       "fitted to sample_ankle_dyn_mri.nii.gz (352x352x6x15, xyzt coords), Adam lr 5e-3",
+           "batch_per_gpu": 1 << args.batch_log2, "global_batch": (1 << args.batch_log2) * args.gpus,
+           "parallelism": f"dp{args.gpus}", "l2": "inputs larger than L2: Adam streams 428 MB of p/g/m/v every step "
+                                                  "(tables+grads+moments 244 MB > 126 MB L2)"}
+    if cpu_sample:
+        cfg["cpu_sample_coords_per_step"] = cpu_sample
+    return cfg
+
+
+# -------------------------------------------------------------------------------------------------- B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from mri_interpolation_b200 import _lib, distributed, models, nifti, sweep
+    from mri_interpolation_b200 import functional as Fn
+
+    rank, local_rank, world = distributed.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    torch.manual_seed(1337)
+    model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
+    opt = model.configure_optimizers()
+    vol = nifti.load(SAMPLE).get_fdata(np.float32)
+    pix = torch.from_numpy(vol).flatten()
+    pix = ((pix - pix.min()) / (pix.max() - pix.min())).to(dev)
+    sampler = Fn.VoxelSampler(pix, vol.shape)
+    n = 1 << args.batch_log2
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1337 + rank)
+    total_steps = args.steps + args.warmup
+    # the epoch's shuffled index stream is drawn up front (like a DataLoader sampler); slicing it is free
+    index = torch.randint(0, sampler.total, (total_steps, n), device=dev, generator=gen)
+
+    def step(i):
+        x, y = sampler.batch(index[i])
+        loss = model.training_step((x, y), i)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.warmup, total_steps):
+        loss = step(i)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count - launches0
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n * world / (ms_step * 1e-3)
+    final_loss = float(loss)
+
+    # ---- e2e: host batches through the public API
+    host_x = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    host_y = torch.empty((n, 1), dtype=torch.float32).pin_memory()
+    x0, y0 = sampler.batch(index[0])
+    host_x.copy_(x0.cpu()); host_y.copy_(y0.cpu())
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step(i):
+        xb = host_x.to(dev, non_blocking=True)
+        yb = host_y.to(dev, non_blocking=True)
+        l = model.training_step((xb, yb), i)
+        l.backward()
+        opt.step()
+        opt.zero_grad()
+        return float(l)  # D2H read of the loss every step
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = n * world / float(e2e_dt.item())
+
+    # ---- isolated kernel timings for the roofline (rank 0, L2 flushed between launches)
+    roof, kern, infer = None, None, None
+    if rank == 0:
+        peak, peak_src = peaks()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        enc = model.encoder
+        x, y = sampler.batch(index[0])
+        go = torch.randn(n, 32, device=dev)
+
+        def timed(fn, reps=10):
+            times = []
+            for _ in range(3):
+                fn()
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                times.append(a.elapsed_time(b))
+            return float(np.mean(times)), float(np.min(times))
+
+        with torch.no_grad():
+            fwd_ms, fwd_min = timed(lambda: enc(x))
+        enc_out = enc(x)
+
+        def bwd():
+            torch.autograd.backward(enc_out, go, retain_graph=True)
+        bwd_ms, bwd_min = timed(bwd)
+        opt.arena.grad.zero_()
+        adam_ms, adam_min = timed(lambda: opt.step())
+        hash_bytes = HASH_BYTES_PER_COORD * n
+        adam_bytes = 32 * opt.arena.numel  # p,g,m,v read; p,m,v,g written (fused gradient clear)
+        kern = {
+            "hashgrid_fwd": {"ms": fwd_ms, "GBps_algorithmic": hash_bytes / fwd_ms / 1e6, "frac": hash_bytes / fwd_ms / 1e6 / peak},
+            "hashgrid_bwd": {"ms": bwd_ms, "GBps_algorithmic": hash_bytes / bwd_ms / 1e6, "frac": hash_bytes / bwd_ms / 1e6 / peak},
+            "adam_step": {"ms": adam_ms, "GBps_algorithmic": adam_bytes / adam_ms / 1e6, "frac": adam_bytes / adam_ms / 1e6 / peak},
+        }
+        top = "hashgrid_bwd" if bwd_ms >= fwd_ms else "hashgrid_fwd"
+        roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": peak, "unit": "GB/s",
+                "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": hash_bytes,
+                "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding); tables (61 MB) fit in "
+                        "the 126 MB L2, so DRAM traffic is far below the algorithmic bytes - see profiles/"}
+        # ---- inference: fused dense-grid sweep (config 3), voxels/s
+        if not args.no_infer:
+            total_vox = int(np.prod(SWEEP_SHAPE))
+            for _ in range(2):
+                sweep.dense_sweep(model, SWEEP_SHAPE)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            reps = 3
+            for _ in range(reps):
+                out = sweep.dense_sweep(model, SWEEP_SHAPE)
+            b.record(); torch.cuda.synchronize()
+            sw_ms = a.elapsed_time(b) / reps
+            t1 = time.perf_counter()
+            host = out.reshape(SWEEP_SHAPE).cpu()
+            d2h_s = time.perf_counter() - t1
+            infer = {"metric": "infer_voxels_per_s", "value": total_vox / (sw_ms * 1e-3), "unit": "voxels/s",
+                     "workload": f"fused hash+decoder sweep of {SWEEP_SHAPE} ({total_vox} voxels), 1 GPU slab",
+                     "ms": sw_ms, "e2e_value_with_d2h": total_vox / (sw_ms * 1e-3 + d2h_s)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, dt, ncpu = time_oracle(args.cpu_batch_log2, 3, 1)
+        cpu = {"value": v, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"3 steps of 2^{args.cpu_batch_log2} coords of the same training step (oracle port of the "
+                         f"reference's PyTorch CPU path), {dt * 1e3:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32",
+            "data": "sample_ankle_dyn_mri.nii.gz (bundled reference sample volume), random-init weights (seed 1337)",
+            "config": workload_config(args), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": n * 20, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps},
+            "gpu_launches": launches, "final_loss": final_loss,
+            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "infer": infer,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -117,6 +117,12 @@ int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t
 int mri_grid_coords(const float* axes, const int32_t* host_shape, int dim, int64_t first,
                     int64_t count, float* coords, void* stream);
 
+/* Training batch from voxel indices (MriImage semantics, datamodules.py:130-172): coords[i,:] are the
+ * grid coordinates of flat C-order voxel index[i] (synthesised, no coordinate table), values[i] =
+ * pixels[index[i]].  index is int64 on the device; pixels/values may both be NULL. */
+int mri_gather_voxels(const float* axes, const int32_t* host_shape, int dim, const int64_t* index,
+                      int64_t count, const float* pixels, float* coords, float* values, void* stream);
+
 /* Fused sweep of a hash-grid + MLP-decoder model (models.py:741-751 intended forward, nb cell 37):
  * voxel index -> coordinates -> all-level encoding -> decoder, nothing but `out` (count x m_out)
  * is written.  Decoder = n_dense layers of Linear+act, parameters packed as

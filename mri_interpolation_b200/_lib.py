@@ -50,6 +50,7 @@ SIGNATURES = {
     "mri_mse_loss_grad": [_P, _P, _I64, _F, _P, _P, _P],
     "mri_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _I, _P],
     "mri_grid_coords": [_P, ctypes.POINTER(ctypes.c_int32), _I, _I64, _I64, _P, _P],
+    "mri_gather_voxels": [_P, ctypes.POINTER(ctypes.c_int32), _I, _P, _I64, _P, _P, _P, _P],
     "mri_hashmlp_sweep": [_P, ctypes.POINTER(ctypes.c_int32), _I, _I64, _I64, _P, ctypes.POINTER(Level), _I, _I, _P,
                           ctypes.POINTER(ctypes.c_int32), _I, _I, _I, _P, _P],
 }
@@ -108,9 +109,10 @@ def check(status: int, what: str = "") -> None:
         raise MriB200Error(f"{what} failed (status {status}): {msg.decode() if msg else ''}")
 
 
-def call(name: str, *args) -> None:
+def call(name: str, *args, kernels: int = 1) -> None:
+    """Invoke a C-ABI entry point; `kernels` = CUDA kernels that call launches (for bench.py's count)."""
     global launch_count
-    launch_count += 1
+    launch_count += kernels
     check(getattr(lib(), name)(*args), name)
 
 

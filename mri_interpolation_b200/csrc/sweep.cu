@@ -40,6 +40,28 @@ __global__ void __launch_bounds__(256) grid_coords_kernel(const float* __restric
   for (int d = 0; d < D; ++d) coords[i * D + d] = v[d];
 }
 
+// Training batch from voxel indices: coordinates synthesised from the flat index (no (M, D) coordinate
+// table in HBM), intensities gathered from the normalised volume (datamodules.py:130-172 semantics).
+template <int D>
+__global__ void __launch_bounds__(256) gather_voxels_kernel(const float* __restrict__ axes, const GridDesc gd,
+                                                            const int64_t* __restrict__ index, const float* __restrict__ pixels,
+                                                            int64_t count, float* __restrict__ coords, float* __restrict__ values) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t v = __ldg(index + i);
+  float xv[D];
+  voxel_coord<D>(axes, gd, v, xv);
+  if constexpr (D == 4) {
+    reinterpret_cast<float4*>(coords)[i] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+  } else if constexpr (D == 2) {
+    reinterpret_cast<float2*>(coords)[i] = make_float2(xv[0], xv[1]);
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) coords[i * D + d] = xv[d];
+  }
+  if (values) values[i] = __ldg(pixels + v);
+}
+
 template <int F>
 __device__ __forceinline__ void gather_feat(const float* __restrict__ row, float (&r)[F]) {
   if constexpr (F == 1) {
@@ -209,6 +231,29 @@ extern "C" int mri_grid_coords(const float* axes, const int32_t* host_shape, int
     default: grid_coords_kernel<4><<<grid, 256, 0, s>>>(axes, gd, first, count, coords); break;
   }
   MRI_LAUNCH_OK("grid_coords_kernel");
+  return MRI_OK;
+}
+
+extern "C" int mri_gather_voxels(const float* axes, const int32_t* host_shape, int dim, const int64_t* index,
+                                 int64_t count, const float* pixels, float* coords, float* values, void* stream) {
+  if (!axes || !host_shape || !index || !coords) return fail(MRI_ERR_INVALID, "gather_voxels: null pointer");
+  if ((values != nullptr) != (pixels != nullptr)) return fail(MRI_ERR_INVALID, "gather_voxels: pixels and values go together");
+  if (dim < 1 || dim > MRI_MAX_DIM) return fail(MRI_ERR_UNSUPPORTED, "gather_voxels: dim %d not in 1..4", dim);
+  if (count < 0) return fail(MRI_ERR_INVALID, "gather_voxels: negative count");
+  GridDesc gd;
+  int64_t total;
+  int st = make_grid_desc(host_shape, dim, &gd, &total);
+  if (st != MRI_OK) return st;
+  if (count == 0) return MRI_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>((count + 255) / 256);
+  switch (dim) {
+    case 1: gather_voxels_kernel<1><<<grid, 256, 0, s>>>(axes, gd, index, pixels, count, coords, values); break;
+    case 2: gather_voxels_kernel<2><<<grid, 256, 0, s>>>(axes, gd, index, pixels, count, coords, values); break;
+    case 3: gather_voxels_kernel<3><<<grid, 256, 0, s>>>(axes, gd, index, pixels, count, coords, values); break;
+    default: gather_voxels_kernel<4><<<grid, 256, 0, s>>>(axes, gd, index, pixels, count, coords, values); break;
+  }
+  MRI_LAUNCH_OK("gather_voxels_kernel");
   return MRI_OK;
 }
 

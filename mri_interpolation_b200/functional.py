@@ -164,7 +164,8 @@ class DenseFn(torch.autograd.Function):
             gb_direct = _direct_grad(bias)
             gb = gb_direct if gb_direct is not None else torch.zeros_like(bias)
         _lib.call("mri_dense_backward", x2.data_ptr(), x2.stride(0), weight.data_ptr(), _lib.ptr(pre), gy.data_ptr(),
-                  n, k, m, ctx.act, ctx.w0, dpre.data_ptr(), _lib.ptr(gx), gw.data_ptr(), _lib.ptr(gb), _lib.stream())
+                  n, k, m, ctx.act, ctx.w0, dpre.data_ptr(), _lib.ptr(gx), gw.data_ptr(), _lib.ptr(gb), _lib.stream(),
+                  kernels=3 if gx is not None else 2)
         return (gx.reshape(ctx.x_shape) if gx is not None else None,
                 None if gw_direct is not None else gw,
                 None if (bias is None or gb_direct is not None) else gb,
@@ -221,3 +222,26 @@ def grid_coords(axes: Sequence[torch.Tensor], first: int, count: int, device) ->
     _lib.call("mri_grid_coords", flat_axes.data_ptr(), cshape, len(shape), int(first), int(count), out.data_ptr(),
               _lib.stream())
     return out
+
+
+class VoxelSampler:
+    """Device-resident volume -> training batches from voxel indices (coordinates synthesised in-kernel)."""
+
+    def __init__(self, pixels: torch.Tensor, shape: Sequence[int], norm_siren: bool = False):
+        from .datamodules import mgrid_axes
+        import ctypes
+        self.pixels = _lib.require_cuda_f32(pixels, "pixels").reshape(-1).contiguous()
+        self.shape = [int(s) for s in shape]
+        self.axes = torch.cat(mgrid_axes(self.shape, norm_siren)).to(pixels.device)
+        self._cshape = (ctypes.c_int32 * len(self.shape))(*self.shape)
+        self.total = int(self.pixels.numel())
+
+    def batch(self, index: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if index.dtype != torch.int64 or not index.is_cuda:
+            raise MriB200Error("VoxelSampler.batch: index must be a CUDA int64 tensor")
+        n = index.numel()
+        x = torch.empty((n, len(self.shape)), device=index.device, dtype=torch.float32)
+        y = torch.empty((n, 1), device=index.device, dtype=torch.float32)
+        _lib.call("mri_gather_voxels", self.axes.data_ptr(), self._cshape, len(self.shape), index.data_ptr(), n,
+                  self.pixels.data_ptr(), x.data_ptr(), y.data_ptr(), _lib.stream())
+        return x, y

@@ -134,3 +134,17 @@ def test_short_fit_on_ankle_slice_psnr_parity(tmp_path):
     assert psnr_ref > 20.0  # the fit actually learned something
     assert abs(psnr_ref - psnr_gpu) < 0.1  # north_star: within 0.1 dB at a fixed step count
     assert abs(ssim_ref - ssim_gpu) < 0.01
+
+
+def test_voxel_sampler_matches_mriimage_semantics():
+    from mri_interpolation_b200 import functional as Fn
+    from oracle import sweep as osweep
+    shape = (9, 8, 3, 5)
+    gen = torch.Generator().manual_seed(4)
+    vol = torch.rand(shape, generator=gen)
+    pixels = osweep.normalise_intensities(vol)
+    coords = osweep.grid_coords(shape)
+    idx = torch.randint(0, coords.shape[0], (5000,), generator=gen)
+    s = Fn.VoxelSampler(pixels.to(DEV), shape)
+    x, y = s.batch(idx.to(DEV))
+    assert torch.equal(x.cpu(), coords[idx]) and torch.equal(y.cpu(), pixels[idx])
