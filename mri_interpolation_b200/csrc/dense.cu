@@ -178,6 +178,7 @@ using namespace mri;
 
 extern "C" int mri_dense_forward(const float* x, int64_t ldx, const float* w, const float* b, int64_t n, int k, int m,
                                  int act, float w0, float* y, float* pre, void* stream) {
+  if (n == 0 && w) return MRI_OK;
   if (!x || !w || !y) return fail(MRI_ERR_INVALID, "dense_forward: null pointer");
   if (n < 0 || k < 1 || m < 1 || ldx < k) return fail(MRI_ERR_INVALID, "dense_forward: bad sizes n=%lld k=%d m=%d ldx=%lld",
                                                       (long long)n, k, m, (long long)ldx);
@@ -203,6 +204,7 @@ extern "C" int mri_dense_forward(const float* x, int64_t ldx, const float* w, co
 extern "C" int mri_dense_backward(const float* x, int64_t ldx, const float* w, const float* pre, const float* grad_y,
                                   int64_t n, int k, int m, int act, float w0, float* dpre, float* grad_x, float* grad_w,
                                   float* grad_b, void* stream) {
+  if (n == 0 && w && grad_w) return MRI_OK;
   if (!x || !w || !grad_y || !dpre || !grad_w) return fail(MRI_ERR_INVALID, "dense_backward: null pointer");
   if (act != MRI_ACT_IDENTITY && !pre) return fail(MRI_ERR_INVALID, "dense_backward: pre-activation required");
   if (n < 0 || k < 1 || m < 1 || ldx < k) return fail(MRI_ERR_INVALID, "dense_backward: bad sizes");

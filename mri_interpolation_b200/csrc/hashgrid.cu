@@ -169,8 +169,8 @@ int launch_bwd(const float* x, const float* go, const LevelTable& T, int64_t n, 
 }
 
 int check_common(const void* x, int64_t n, int dim, const mri_level_t* lv, int n_levels, int n_features) {
-  if (!x || !lv) return fail(MRI_ERR_INVALID, "hashgrid: null pointer");
   if (n < 0) return fail(MRI_ERR_INVALID, "hashgrid: negative n");
+  if ((!x && n > 0) || !lv) return fail(MRI_ERR_INVALID, "hashgrid: null pointer");
   if (dim < 2 || dim > MRI_MAX_DIM) return fail(MRI_ERR_UNSUPPORTED, "hashgrid: dim %d not in 2..4", dim);
   if (n_levels < 1 || n_levels > MRI_MAX_LEVELS)
     return fail(MRI_ERR_UNSUPPORTED, "hashgrid: n_levels %d not in 1..%d", n_levels, MRI_MAX_LEVELS);
@@ -225,6 +225,7 @@ extern "C" int mri_hashgrid_forward(const float* x, int64_t n, int dim, const fl
                                     void* stream) {
   int st = check_common(x, n, dim, host_levels, n_levels, n_features);
   if (st != MRI_OK) return st;
+  if (n == 0) return MRI_OK;  // empty batch: nothing to do (pointers of empty tensors may be null)
   if (!tables || !out) return fail(MRI_ERR_INVALID, "hashgrid_forward: null tables/out");
   if ((reinterpret_cast<uintptr_t>(tables) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
     return fail(MRI_ERR_INVALID, "hashgrid_forward: tables/out must be 16-byte aligned");
@@ -245,6 +246,7 @@ extern "C" int mri_hashgrid_backward(const float* x, int64_t n, int dim, const f
                                      const mri_level_t* host_levels, int n_levels, int n_features, void* stream) {
   int st = check_common(x, n, dim, host_levels, n_levels, n_features);
   if (st != MRI_OK) return st;
+  if (n == 0) return MRI_OK;
   if (!grad_out || !grad_tables) return fail(MRI_ERR_INVALID, "hashgrid_backward: null grad pointer");
   if ((reinterpret_cast<uintptr_t>(grad_tables) & 15) || (reinterpret_cast<uintptr_t>(grad_out) & 15))
     return fail(MRI_ERR_INVALID, "hashgrid_backward: grads must be 16-byte aligned");

@@ -12,7 +12,7 @@ namespace {
 
 struct AdamArgs {
   float step_size;      // lr / (1 - beta1^t)
-  float inv_bc2_sqrt;   // 1 / sqrt(1 - beta2^t)
+  float bc2_sqrt;       // sqrt(1 - beta2^t)
   float beta1, beta2, one_minus_beta1, one_minus_beta2;
   float eps, weight_decay, grad_scale;
   int zero_grad;
@@ -25,8 +25,8 @@ __device__ __forceinline__ void adam_update(float& p, float& g, float& m, float&
   if (a.weight_decay != 0.0f) gg = fmaf(a.weight_decay, p, gg);
   m = fmaf(a.one_minus_beta1, gg - m, m);
   v = fmaf(a.one_minus_beta2 * gg, gg, v * a.beta2);
-  const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
-  p = p - a.step_size * (m / denom);
+  const float denom = __fdiv_rn(sqrtf(v), a.bc2_sqrt) + a.eps;  // torch: (sqrt(v) / sqrt(bc2)).add_(eps)
+  p = p - a.step_size * __fdiv_rn(m, denom);                    // torch: p.addcdiv_(m, denom, value=-lr/bc1)
   if (a.zero_grad) g = 0.0f;
 }
 
@@ -106,7 +106,7 @@ extern "C" int mri_adam_step(float* p, float* g, float* m, float* v, int64_t cou
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   AdamArgs a;
   a.step_size = static_cast<float>(lr / bc1);
-  a.inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
+  a.bc2_sqrt = static_cast<float>(sqrt(bc2));
   a.beta1 = static_cast<float>(beta1);
   a.beta2 = static_cast<float>(beta2);
   a.one_minus_beta1 = static_cast<float>(1.0 - beta1);
