@@ -93,6 +93,25 @@ int mri_dense_backward(const float* x, int64_t ldx, const float* w, const float*
                        const float* grad_y, int64_t n, int k, int m, int act, float w0,
                        float* dpre, float* grad_x, float* grad_w, float* grad_b, void* stream);
 
+/* ---- wide SIREN layers on tcgen05 tensor cores ------------------------------------------------ */
+
+/* 1 if a layer with `k` inputs and `m` outputs is taken by the tcgen05 path (multiples of 64). */
+int mri_siren_tc_supported(int k, int m);
+
+/* fp32 -> two bf16 planes, x = hi + lo (hi = bf16(x), lo = bf16(x - hi)); lo may be NULL. */
+int mri_siren_tc_split(const float* src, int64_t count, void* hi, void* lo, void* stream);
+
+/* One dense layer on the tensor cores (SirenLayer.forward, models.py:153-156, and its dgrad):
+ *   acc[n, j] = sum_k A[n, k] W[j, k]   A = (a_hi [+ a_lo]) (n, k) bf16, W = (w_hi [+ w_lo]) (m, k) bf16
+ *   passes = 3: A_hi W_hi + A_lo W_hi + A_hi W_lo (fp32-parity mode);  passes = 1: bf16 mode
+ *   pre = acc + bias;  out = act == SINE ? sin(w0 pre) : pre;  aux = w0 cos(w0 pre) (SINE only)
+ *   out *= mul (optional, (n, m) f32) - used by the backward pass: dPre_prev = (dPre W) * act'_prev
+ * Outputs (each optional): out_hi/out_lo bf16 planes (next layer's A operand), out_f32, aux_f32. */
+int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                       const float* bias, int64_t n, int k, int m, int act, float w0, int passes,
+                       const float* mul, void* out_hi, void* out_lo, float* out_f32, float* aux_f32,
+                       void* stream);
+
 /* ---- loss / optimiser ------------------------------------------------------------------ */
 
 /* F.mse_loss(y, y_pred) (models.py:64): *loss += sum((pred-target)^2) * inv_count and

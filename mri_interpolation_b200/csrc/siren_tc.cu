@@ -1,0 +1,442 @@
+// Wide SIREN layers on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   D[n, j] = sum_k A[n, k] * B[j, k]        A = activations (rows = coordinates), B = weights (K-major both)
+//
+// fp32 parity on bf16 tensor cores: every fp32 operand is stored as two bf16 planes, x = hi + lo
+// (hi = bf16(x), lo = bf16(x - hi)); the product is accumulated in fp32 TMEM as
+//   A_hi*B_hi + A_lo*B_hi + A_hi*B_lo          (3 tcgen05.mma per K-slice, "passes = 3")
+// which keeps ~16 mantissa bits per operand (dropped term ~2^-18).  passes = 1 is the plain bf16 mode.
+//
+// Kernel structure (persistent, one CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 K-elements) into a ring of
+//              smem stages, completion on "full" mbarriers
+//   warp 1     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16) against
+//              smem descriptors, tcgen05.commit frees the stage ("empty") and publishes the accumulator
+//   warps 2-5  epilogue: tcgen05.ld the 128 x block_n fp32 accumulator out of TMEM (double-buffered: 2 x
+//              block_n columns), + bias, sin(w0 .) / w0 cos(w0 .) or * mul, stores bf16 hi/lo planes + f32
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mri {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct LayerParams {
+  int64_t n_rows;
+  int k, m, block_n, passes, stages;
+  int num_m_tiles, num_n_tiles;
+  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;
+  int act;
+  float w0;
+  const float* bias;       // (m) or null
+  const float* mul;        // (n_rows, m) or null: elementwise factor applied to the result (dgrad: act')
+  __nv_bfloat16* out_hi;   // (n_rows, m) or null
+  __nv_bfloat16* out_lo;   // (n_rows, m) or null
+  float* out_f32;          // (n_rows, m) or null
+  float* aux_f32;          // (n_rows, m) or null: w0*cos(w0*pre) for the backward pass
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= static_cast<uint64_t>(1) << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> f32, both operands K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---- the GEMM + fused epilogue ------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                      const LayerParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.k / BLOCK_K;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t tmem_cols = 2u * static_cast<uint32_t>(p.block_n);  // power of two >= 128 (block_n in {64,128,256})
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (lane == 0) {
+          uint8_t* base = smem + static_cast<size_t>(stage) * p.stage_bytes;
+          mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+          tma_load_2d(base, &map_a_hi, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+          uint8_t* bptr = base + p.a_plane_bytes;
+          if (p.passes == 3) {
+            tma_load_2d(bptr, &map_a_lo, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+            bptr += p.a_plane_bytes;
+          }
+          tma_load_2d(bptr, &map_b_hi, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+          if (p.passes == 3)
+            tma_load_2d(bptr + p.b_plane_bytes, &map_b_lo, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc_stage], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc_stage * p.block_n);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+          const uint32_t a_lo = a_hi + p.a_plane_bytes;
+          const uint32_t b_hi = a_hi + (p.passes == 3 ? 2 : 1) * p.a_plane_bytes;
+          const uint32_t b_lo = b_hi + p.b_plane_bytes;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 2;  // bytes along the swizzled 128-byte row
+            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
+            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+            if (p.passes == 3) {
+              // small cross terms first, then the dominant hi*hi term
+              tcgen05_mma_f16(d_tmem, make_kmajor_sw128_desc(a_lo + koff), db_hi, idesc, (kb | ks) != 0);
+              tcgen05_mma_f16(d_tmem, da_hi, make_kmajor_sw128_desc(b_lo + koff), idesc, 1);
+              tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+            } else {
+              tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
+            }
+          }
+          tcgen05_commit(&empty_bar[stage]);                            // smem stage reusable once these MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc_stage]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    int acc_stage = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
+      tcgen05_fence_after();
+      const int64_t row = static_cast<int64_t>(m_tile) * BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.n_rows;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc_stage * p.block_n + c0);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int col0 = n_tile * p.block_n + c0;
+          const int64_t off = row * p.m + col0;
+          float out[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float acc = __uint_as_float(v[j]);
+            if (p.bias) acc += __ldg(p.bias + col0 + j);
+            out[j] = acc;
+          }
+          if (p.act == MRI_ACT_SINE) {
+            float aux[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = reduce_2pi(p.w0 * out[j]);
+              aux[j] = p.w0 * __cosf(r);
+              out[j] = __sinf(r);
+            }
+            if (p.aux_f32) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(p.aux_f32 + off)[q] = make_float4(aux[4 * q], aux[4 * q + 1], aux[4 * q + 2], aux[4 * q + 3]);
+            }
+          }
+          if (p.mul) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(p.mul + off) + q);
+              out[4 * q] *= f.x; out[4 * q + 1] *= f.y; out[4 * q + 2] *= f.z; out[4 * q + 3] *= f.w;
+            }
+          }
+          if (p.out_f32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(p.out_f32 + off)[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+          }
+          if (p.out_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = out[2 * j], b = out[2 * j + 1];
+              const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+              hi[j] = pack_bf16x2(a, b);
+              lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              reinterpret_cast<uint4*>(p.out_hi + off)[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            if (p.out_lo) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<uint4*>(p.out_lo + off)[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc_stage]);
+      if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// fp32 -> (hi, lo) bf16 planes
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ src, int64_t count, __nv_bfloat16* __restrict__ hi,
+                                                    __nv_bfloat16* __restrict__ lo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float x = src[i];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major (rows, cols) tensor, box = (box_rows, 64 cols), SWIZZLE_128B
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MRI_ERR_CUDA, "siren_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BLOCK_K), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MRI_ERR_CUDA, "siren_tc: cuTensorMapEncodeTiled failed with %d", static_cast<int>(r));
+  return MRI_OK;
+}
+
+int pick_block_n(int m) {
+  if (m % 256 == 0) return 256;
+  if (m % 128 == 0) return 128;
+  if (m % 64 == 0) return 64;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_siren_tc_supported(int k, int m) {
+  return (k >= 64 && k % 64 == 0 && tc::pick_block_n(m) != 0) ? 1 : 0;
+}
+
+extern "C" int mri_siren_tc_split(const float* src, int64_t count, void* hi, void* lo, void* stream) {
+  if (!src || !hi) return fail(MRI_ERR_INVALID, "siren_tc_split: null pointer");
+  if (count < 0) return fail(MRI_ERR_INVALID, "siren_tc_split: negative count");
+  if (count == 0) return MRI_OK;
+  int64_t want = (count + 255) / 256;
+  const int64_t cap = 16LL * sm_count();
+  if (want > cap) want = cap;
+  tc::split_kernel<<<static_cast<int>(want), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, count, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+  MRI_LAUNCH_OK("split_kernel");
+  return MRI_OK;
+}
+
+extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                  int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
+                                  void* out_lo, float* out_f32, float* aux_f32, void* stream) {
+  if (!a_hi || !w_hi) return fail(MRI_ERR_INVALID, "siren_tc_layer: null operand");
+  if (passes != 1 && passes != 3) return fail(MRI_ERR_INVALID, "siren_tc_layer: passes must be 1 (bf16) or 3 (split fp32)");
+  if (passes == 3 && (!a_lo || !w_lo)) return fail(MRI_ERR_INVALID, "siren_tc_layer: lo planes required for passes=3");
+  if (!mri_siren_tc_supported(k, m)) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: k=%d m=%d not tileable (need multiples of 64)", k, m);
+  if (act != MRI_ACT_IDENTITY && act != MRI_ACT_SINE) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: activation %d", act);
+  if (n < 0) return fail(MRI_ERR_INVALID, "siren_tc_layer: negative n");
+  if (n == 0) return MRI_OK;
+  if (!out_hi && !out_f32) return fail(MRI_ERR_INVALID, "siren_tc_layer: no output requested");
+
+  tc::LayerParams p{};
+  p.n_rows = n; p.k = k; p.m = m; p.passes = passes; p.act = act; p.w0 = w0;
+  p.block_n = tc::pick_block_n(m);
+  p.num_m_tiles = static_cast<int>((n + tc::BLOCK_M - 1) / tc::BLOCK_M);
+  p.num_n_tiles = m / p.block_n;
+  p.a_plane_bytes = tc::BLOCK_M * tc::BLOCK_K * 2;
+  p.b_plane_bytes = static_cast<uint32_t>(p.block_n) * tc::BLOCK_K * 2;
+  p.stage_bytes = static_cast<uint32_t>(passes == 3 ? 2 : 1) * (p.a_plane_bytes + p.b_plane_bytes);
+  const int budget = tc::SMEM_LIMIT - 2048;
+  p.stages = budget / static_cast<int>(p.stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: tile does not fit shared memory");
+  p.bias = bias; p.mul = mul;
+  p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+  p.out_f32 = out_f32; p.aux_f32 = aux_f32;
+
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int st;
+  if ((st = tc::make_map(&ma_hi, a_hi, n, k, tc::BLOCK_M)) != MRI_OK) return st;
+  if ((st = tc::make_map(&ma_lo, passes == 3 ? a_lo : a_hi, n, k, tc::BLOCK_M)) != MRI_OK) return st;
+  if ((st = tc::make_map(&mb_hi, w_hi, m, k, p.block_n)) != MRI_OK) return st;
+  if ((st = tc::make_map(&mb_lo, passes == 3 ? w_lo : w_hi, m, k, p.block_n)) != MRI_OK) return st;
+
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  MRI_CUDA_OK(cudaFuncSetAttribute(tc::siren_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  tc::siren_tc_layer_kernel<<<grid, tc::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  MRI_LAUNCH_OK("siren_tc_layer_kernel");
+  return MRI_OK;
+}
