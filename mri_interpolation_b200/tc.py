@@ -1,0 +1,48 @@
+"""Thin Python handles over the tcgen05 SIREN-layer entry points (csrc/siren_tc.cu).
+
+Operands live as two bf16 planes (hi, lo) with x = hi + lo; ``passes=3`` multiplies them as
+A_hi W_hi + A_lo W_hi + A_hi W_lo in fp32 TMEM accumulators (fp32-parity mode), ``passes=1`` is plain bf16.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDENTITY, ACT_SINE, MriB200Error
+
+
+def supported(k: int, m: int) -> bool:
+    return bool(_lib.lib().mri_siren_tc_supported(int(k), int(m)))
+
+
+def split(x: torch.Tensor, need_lo: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """fp32 tensor -> (hi, lo) bf16 planes of the same shape."""
+    _lib.require_cuda_f32(x, "split input")
+    x = x.contiguous()
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if need_lo else None
+    _lib.call("mri_siren_tc_split", x.data_ptr(), x.numel(), hi.data_ptr(), _lib.ptr(lo), _lib.stream())
+    return hi, lo
+
+
+def layer(a_hi, a_lo, w_hi, w_lo, bias, act: int, w0: float, passes: int = 3, mul=None, want_planes: bool = True,
+          want_f32: bool = False, want_aux: bool = False):
+    """acc = A W^T (+bias) on the tensor cores with the fused epilogue; returns (out_hi, out_lo, out_f32, aux)."""
+    n, k = a_hi.shape
+    m = w_hi.shape[0]
+    if w_hi.shape[1] != k:
+        raise MriB200Error(f"tc.layer: A is (n,{k}) but W is {tuple(w_hi.shape)}")
+    for t in (a_hi, a_lo, w_hi, w_lo):
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous()):
+            raise MriB200Error("tc.layer: operands must be contiguous CUDA bf16 planes")
+    dev = a_hi.device
+    out_hi = torch.empty((n, m), device=dev, dtype=torch.bfloat16) if want_planes else None
+    out_lo = torch.empty((n, m), device=dev, dtype=torch.bfloat16) if (want_planes and passes == 3) else None
+    out_f32 = torch.empty((n, m), device=dev, dtype=torch.float32) if want_f32 else None
+    aux = torch.empty((n, m), device=dev, dtype=torch.float32) if want_aux else None
+    _lib.call("mri_siren_tc_layer", a_hi.data_ptr(), _lib.ptr(a_lo), w_hi.data_ptr(), _lib.ptr(w_lo), _lib.ptr(bias),
+              n, k, m, int(act), float(w0), int(passes), _lib.ptr(mul), _lib.ptr(out_hi), _lib.ptr(out_lo),
+              _lib.ptr(out_f32), _lib.ptr(aux), _lib.stream())
+    return out_hi, out_lo, out_f32, aux
