@@ -112,6 +112,16 @@ int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, con
                        const float* mul, void* out_hi, void* out_lo, float* out_f32, float* aux_f32,
                        void* stream);
 
+/* Weight/bias gradient of the layer above on the tensor cores (autograd of models.py:153-156):
+ *   grad_w[j, i] += sum_n G[n, j] X[n, i]   G = dPre planes (n, m), X = layer-input planes (n, k)
+ *   grad_b[j]    += sum_n G[n, j]           (grad_b may be NULL)
+ * Split-K over the batch with fp32 TMEM accumulation; needs m % 128 == 0 and k % 64 == 0. */
+int mri_siren_tc_wgrad(const void* g_hi, const void* g_lo, const void* x_hi, const void* x_lo, int64_t n,
+                       int k, int m, int passes, float* grad_w, float* grad_b, void* stream);
+
+/* (hi, lo) bf16 planes of a * b (b may be NULL): dPre = dOut * act' at the head of the backward pass. */
+int mri_siren_tc_mul_split(const float* a, const float* b, int64_t count, void* hi, void* lo, void* stream);
+
 /* ---- loss / optimiser ------------------------------------------------------------------ */
 
 /* F.mse_loss(y, y_pred) (models.py:64): *loss += sum((pred-target)^2) * inv_count and

@@ -322,6 +322,185 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   }
 }
 
+
+// ---- weight gradient: dW[j, i] += sum_n G[n, j] * X[n, i]  (both operands MN-major, K = batch) -------
+//
+// G = dPre planes (n, m) and X = layer-input planes (n, k) are row-major with the batch index slowest, so
+// for this GEMM (M = j, N = i, K = n) both tensor-core operands are "MN-major".  TMA boxes of 64 columns x
+// 64 batch rows (SWIZZLE_128B) give the canonical MN-major SW128 layout: 64-element MN groups LBO bytes
+// apart, 8-row K groups 1024 B apart.  Split-K over the batch: grid = tiles x splits, each CTA reduces its
+// slice of the batch in TMEM and adds the 128 x block_n partial tile into dW with red.global.add.f32.
+struct WgradParams {
+  int64_t n_rows;
+  int m, k, block_n, passes, stages;
+  int num_m_tiles, num_n_tiles, splits;
+  int64_t rows_per_split;  // multiple of 64
+  uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;
+  float* grad_w;  // (m, k) f32, accumulated
+};
+
+constexpr int WG_BLOCK_K = 64;  // batch rows per stage
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // stride between 64-element MN groups
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mnmajor(int m, int n) {
+  return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+siren_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
+                      const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                      const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tile = blockIdx.x % tiles;
+  const int split = blockIdx.x / tiles;
+  const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+  const int64_t row_begin = static_cast<int64_t>(split) * p.rows_per_split;
+  int64_t row_end = row_begin + p.rows_per_split;
+  if (row_end > p.n_rows) row_end = p.n_rows;
+  const int num_kb = row_end > row_begin ? static_cast<int>((row_end - row_begin + WG_BLOCK_K - 1) / WG_BLOCK_K) : 0;
+  const uint32_t tmem_cols = p.block_n < 32 ? 32u : static_cast<uint32_t>(p.block_n);
+  const int a_groups = BLOCK_M / 64, b_groups = p.block_n / 64;
+  constexpr uint32_t GROUP_BYTES = WG_BLOCK_K * 128;  // one 64-column x 64-row box
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (lane == 0) {
+        uint8_t* base = smem + static_cast<size_t>(stage) * p.stage_bytes;
+        const int r0 = static_cast<int>(row_begin + static_cast<int64_t>(kb) * WG_BLOCK_K);
+        mbar_expect_tx(&full_bar[stage], p.stage_bytes);
+        uint8_t* dst = base;
+        for (int g = 0; g < a_groups; ++g, dst += GROUP_BYTES) tma_load_2d(dst, &map_g_hi, &full_bar[stage], m_tile * BLOCK_M + g * 64, r0);
+        if (p.passes == 3)
+          for (int g = 0; g < a_groups; ++g, dst += GROUP_BYTES) tma_load_2d(dst, &map_g_lo, &full_bar[stage], m_tile * BLOCK_M + g * 64, r0);
+        for (int g = 0; g < b_groups; ++g, dst += GROUP_BYTES) tma_load_2d(dst, &map_x_hi, &full_bar[stage], n_tile * p.block_n + g * 64, r0);
+        if (p.passes == 3)
+          for (int g = 0; g < b_groups; ++g, dst += GROUP_BYTES) tma_load_2d(dst, &map_x_lo, &full_bar[stage], n_tile * p.block_n + g * 64, r0);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16_mnmajor(BLOCK_M, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + static_cast<size_t>(stage) * p.stage_bytes);
+        const uint32_t a_lo = a_hi + p.a_plane_bytes;
+        const uint32_t b_hi = a_hi + (p.passes == 3 ? 2 : 1) * p.a_plane_bytes;
+        const uint32_t b_lo = b_hi + p.b_plane_bytes;
+#pragma unroll
+        for (int ks = 0; ks < WG_BLOCK_K / UMMA_K; ++ks) {
+          const uint32_t koff = ks * UMMA_K * 128;  // 16 batch rows of 128 B
+          const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff, GROUP_BYTES);
+          const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff, GROUP_BYTES);
+          if (p.passes == 3) {
+            tcgen05_mma_f16(tmem_base, make_mnmajor_sw128_desc(a_lo + koff, GROUP_BYTES), db_hi, idesc, (kb | ks) != 0);
+            tcgen05_mma_f16(tmem_base, da_hi, make_mnmajor_sw128_desc(b_lo + koff, GROUP_BYTES), idesc, 1);
+            tcgen05_mma_f16(tmem_base, da_hi, db_hi, idesc, 1);
+          } else {
+            tcgen05_mma_f16(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0);
+          }
+        }
+        tcgen05_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (num_kb > 0) {
+    const int quarter = warp & 3;
+    mbar_wait(&tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int j = m_tile * BLOCK_M + quarter * 32 + lane;  // output row of dW (always < m: m % 128 == 0)
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), v);
+      tmem_ld_wait();
+      float* dst = p.grad_w + static_cast<int64_t>(j) * p.k + n_tile * p.block_n + c0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                   __uint_as_float(v[4 * q + 3]));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// column sums of a (hi [+ lo]) bf16 plane pair: out[j] += sum_n (hi + lo)[n, j]   (bias gradient)
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                                            int64_t n, int m, int64_t rows_per_block, float* __restrict__ out) {
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < n) ? r0 + rows_per_block : n;
+  for (int j = threadIdx.x; j < m; j += 256) {
+    float acc = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) {
+      acc += __bfloat162float(hi[r * m + j]);
+      if (lo) acc += __bfloat162float(lo[r * m + j]);
+    }
+    red_add_f32(out + j, acc);
+  }
+}
+
+// (hi, lo) planes of a * b  (first step of the tensor-core backward: dPre = dOut * act')
+__global__ void __launch_bounds__(256) mul_split_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t count,
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float x = a[i] * (b ? b[i] : 1.0f);
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi[i] = h;
+    if (lo) lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+  }
+}
+
 // fp32 -> (hi, lo) bf16 planes
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ src, int64_t count, __nv_bfloat16* __restrict__ hi,
                                                     __nv_bfloat16* __restrict__ lo) {
@@ -355,6 +534,7 @@ EncodeTiledFn encode_fn() {
 
 // 2-D bf16 row-major (rows, cols) tensor, box = (box_rows, 64 cols), SWIZZLE_128B
 int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int box_rows) {
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(MRI_ERR_INVALID, "siren_tc: operand planes must be 16-byte aligned");
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MRI_ERR_CUDA, "siren_tc: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -438,5 +618,71 @@ extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void
   const int grid = tiles < sm_count() ? tiles : sm_count();
   tc::siren_tc_layer_kernel<<<grid, tc::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   MRI_LAUNCH_OK("siren_tc_layer_kernel");
+  return MRI_OK;
+}
+
+extern "C" int mri_siren_tc_wgrad(const void* g_hi, const void* g_lo, const void* x_hi, const void* x_lo, int64_t n, int k,
+                                  int m, int passes, float* grad_w, float* grad_b, void* stream) {
+  if (!g_hi || !x_hi || !grad_w) return fail(MRI_ERR_INVALID, "siren_tc_wgrad: null pointer");
+  if (passes != 1 && passes != 3) return fail(MRI_ERR_INVALID, "siren_tc_wgrad: passes must be 1 or 3");
+  if (passes == 3 && (!g_lo || !x_lo)) return fail(MRI_ERR_INVALID, "siren_tc_wgrad: lo planes required for passes=3");
+  if (m % 128 != 0 || tc::pick_block_n(k) == 0)
+    return fail(MRI_ERR_UNSUPPORTED, "siren_tc_wgrad: need m %% 128 == 0 and k %% 64 == 0 (m=%d k=%d)", m, k);
+  if (n < 0) return fail(MRI_ERR_INVALID, "siren_tc_wgrad: negative n");
+  if (n == 0) return MRI_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  tc::WgradParams p{};
+  p.n_rows = n; p.m = m; p.k = k; p.passes = passes; p.grad_w = grad_w;
+  p.block_n = tc::pick_block_n(k);
+  p.num_m_tiles = m / tc::BLOCK_M;
+  p.num_n_tiles = k / p.block_n;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  const int64_t max_splits = (n + 4 * tc::WG_BLOCK_K - 1) / (4 * tc::WG_BLOCK_K);
+  if (splits > max_splits) splits = static_cast<int>(max_splits);
+  if (splits < 1) splits = 1;
+  int64_t rps = (n + splits - 1) / splits;
+  rps = (rps + tc::WG_BLOCK_K - 1) / tc::WG_BLOCK_K * tc::WG_BLOCK_K;
+  splits = static_cast<int>((n + rps - 1) / rps);
+  p.splits = splits; p.rows_per_split = rps;
+  p.a_plane_bytes = tc::BLOCK_M * tc::WG_BLOCK_K * 2;
+  p.b_plane_bytes = static_cast<uint32_t>(p.block_n) * tc::WG_BLOCK_K * 2;
+  p.stage_bytes = static_cast<uint32_t>(passes == 3 ? 2 : 1) * (p.a_plane_bytes + p.b_plane_bytes);
+  p.stages = (tc::SMEM_LIMIT - 2048) / static_cast<int>(p.stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_wgrad: tile does not fit shared memory");
+  CUtensorMap mg_hi, mg_lo, mx_hi, mx_lo;
+  int st;
+  if ((st = tc::make_map(&mg_hi, g_hi, n, m, tc::WG_BLOCK_K)) != MRI_OK) return st;
+  if ((st = tc::make_map(&mg_lo, passes == 3 ? g_lo : g_hi, n, m, tc::WG_BLOCK_K)) != MRI_OK) return st;
+  if ((st = tc::make_map(&mx_hi, x_hi, n, k, tc::WG_BLOCK_K)) != MRI_OK) return st;
+  if ((st = tc::make_map(&mx_lo, passes == 3 ? x_lo : x_hi, n, k, tc::WG_BLOCK_K)) != MRI_OK) return st;
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  MRI_CUDA_OK(cudaFuncSetAttribute(tc::siren_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  tc::siren_tc_wgrad_kernel<<<tiles * splits, tc::NUM_THREADS, smem, s>>>(mg_hi, mg_lo, mx_hi, mx_lo, p);
+  MRI_LAUNCH_OK("siren_tc_wgrad_kernel");
+  if (grad_b) {
+    int64_t blocks = 4LL * sm_count();
+    int64_t rpb = (n + blocks - 1) / blocks;
+    if (rpb < 8) rpb = 8;
+    blocks = (n + rpb - 1) / rpb;
+    tc::colsum_planes_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(g_hi),
+                                                                     static_cast<const __nv_bfloat16*>(passes == 3 ? g_lo : nullptr),
+                                                                     n, m, rpb, grad_b);
+    MRI_LAUNCH_OK("colsum_planes_kernel");
+  }
+  return MRI_OK;
+}
+
+extern "C" int mri_siren_tc_mul_split(const float* a, const float* b, int64_t count, void* hi, void* lo, void* stream) {
+  if (!a || !hi) return fail(MRI_ERR_INVALID, "siren_tc_mul_split: null pointer");
+  if (count < 0) return fail(MRI_ERR_INVALID, "siren_tc_mul_split: negative count");
+  if (count == 0) return MRI_OK;
+  int64_t want = (count + 255) / 256;
+  const int64_t cap = 16LL * sm_count();
+  if (want > cap) want = cap;
+  tc::mul_split_kernel<<<static_cast<int>(want), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, count, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
+  MRI_LAUNCH_OK("mul_split_kernel");
   return MRI_OK;
 }

@@ -229,8 +229,30 @@ class SirenNet(BaseMLP):
         final_activation = nn.Identity() if not exists(final_activation) else final_activation
         self.last_layer = SirenLayer(dim_in=dim_hidden, dim_out=dim_out, w0=w0, sigma=self.sigma,
                                      use_bias=use_bias, activation=final_activation)
+        # "auto": hidden->hidden layers that fit the tcgen05 tiles (width % 128 == 0) run on the tensor cores in
+        # the split-precision fp32-parity mode "bf16x3"; "fp32" forces the CUDA-core path; "bf16" = 1 MMA/slice.
+        self.precision = kwargs.get("precision", "auto")
+
+    def _tensor_core_mode(self):
+        mode = self.precision
+        if mode == "fp32":
+            return None
+        from . import siren_fused
+        ok = self.__dict__.get("_tc_eligible")
+        if ok is None:
+            ok = siren_fused.eligible(self)
+            self.__dict__["_tc_eligible"] = ok
+        if not ok:
+            if mode in ("bf16x3", "bf16"):
+                raise RuntimeError("this SirenNet does not fit the tensor-core tiles (hidden width % 128 != 0)")
+            return None
+        return "bf16x3" if mode == "auto" else mode
 
     def forward(self, x):
+        mode = self._tensor_core_mode()
+        if mode is not None:
+            from . import siren_fused
+            return siren_fused.forward(self, x, mode)
         for layer in self.layers:
             x = layer(x)
         return self.last_layer(x)

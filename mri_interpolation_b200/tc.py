@@ -46,3 +46,29 @@ def layer(a_hi, a_lo, w_hi, w_lo, bias, act: int, w0: float, passes: int = 3, mu
               n, k, m, int(act), float(w0), int(passes), _lib.ptr(mul), _lib.ptr(out_hi), _lib.ptr(out_lo),
               _lib.ptr(out_f32), _lib.ptr(aux), _lib.stream())
     return out_hi, out_lo, out_f32, aux
+
+
+def mul_split(a: torch.Tensor, b: Optional[torch.Tensor], need_lo: bool = True):
+    """(hi, lo) planes of a * b (b may be None)."""
+    _lib.require_cuda_f32(a, "mul_split input")
+    a = a.contiguous()
+    if b is not None:
+        b = _lib.require_cuda_f32(b, "mul_split factor").contiguous()
+    hi = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16)
+    lo = torch.empty(a.shape, device=a.device, dtype=torch.bfloat16) if need_lo else None
+    _lib.call("mri_siren_tc_mul_split", a.data_ptr(), _lib.ptr(b), a.numel(), hi.data_ptr(), _lib.ptr(lo), _lib.stream())
+    return hi, lo
+
+
+def wgrad_supported(k: int, m: int) -> bool:
+    return m % 128 == 0 and k % 64 == 0 and k >= 64
+
+
+def wgrad(g_hi, g_lo, x_hi, x_lo, grad_w: torch.Tensor, grad_b: Optional[torch.Tensor], passes: int = 3) -> None:
+    """grad_w (m,k) += G^T X ; grad_b (m) += colsum(G) on the tensor cores (split-K over the batch)."""
+    n, m = g_hi.shape
+    k = x_hi.shape[1]
+    if x_hi.shape[0] != n or tuple(grad_w.shape) != (m, k):
+        raise MriB200Error("tc.wgrad: shape mismatch")
+    _lib.call("mri_siren_tc_wgrad", g_hi.data_ptr(), _lib.ptr(g_lo), x_hi.data_ptr(), _lib.ptr(x_lo), n, k, m, int(passes),
+              grad_w.data_ptr(), _lib.ptr(grad_b), _lib.stream(), kernels=2 if grad_b is not None else 1)

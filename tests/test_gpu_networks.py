@@ -104,7 +104,8 @@ def test_hashmlp_batchnorm_variant_matches_reference_vectors():
     net.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in fx.items() if k.startswith("param:")}, strict=False)
     net = net.to(DEV).train()
     x, y = torch.from_numpy(fx["x"]).to(DEV), torch.from_numpy(fx["y"]).to(DEV)
-    pred = net(x)
+    import copy
+    pred = copy.deepcopy(net)(x)  # a second forward on `net` itself would update the running statistics twice
     torch.testing.assert_close(pred.cpu(), torch.from_numpy(fx["pred"]), rtol=RTOL, atol=1e-5)
     net.training_step((x, y), 0).backward()
     scale = max(float(np.abs(fx[f"grad:{n}"]).max()) for n, _ in net.named_parameters() if f"grad:{n}" in fx)
