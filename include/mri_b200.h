@@ -93,6 +93,24 @@ int mri_dense_backward(const float* x, int64_t ldx, const float* w, const float*
                        const float* grad_y, int64_t n, int k, int m, int act, float w0,
                        float* dpre, float* grad_x, float* grad_w, float* grad_b, void* stream);
 
+/* ---- fused 2-layer decoder of the hash-grid models ------------------------------------------------- */
+
+/* 1 if the fused kernels take enc width k0, hidden width h and hidden activation act1. */
+int mri_decoder2_supported(int k0, int h, int act1);
+
+/* y = act2(b2 + w2 . act1(W1 enc + b1)): the HashMLP decoder (models.py:712-739, intended forward nb cell 37)
+ * for n_layers = 2, dim_out = 1.  enc (n, k0); W1 (h, k0); b1 (h); w2 (h) [= Linear(h,1).weight]; b2 (1).
+ * y (n); pre2 (n) or NULL receives the output layer's pre-activation for the backward pass. */
+int mri_decoder2_forward(const float* enc, int64_t n, int k0, int h, const float* w1, const float* b1,
+                         const float* w2, const float* b2, int act1, int act2, float* y, float* pre2,
+                         void* stream);
+
+/* Backward of the above: grad_enc (n, k0) is written; grad_w1/b1/w2/b2 are ACCUMULATED. */
+int mri_decoder2_backward(const float* enc, int64_t n, int k0, int h, const float* w1, const float* b1,
+                          const float* w2, const float* pre2, const float* grad_y, int act1, int act2,
+                          float* grad_enc, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
+                          void* stream);
+
 /* ---- wide SIREN layers on tcgen05 tensor cores ------------------------------------------------ */
 
 /* 1 if a layer with `k` inputs and `m` outputs is taken by the tcgen05 path (multiples of 64). */

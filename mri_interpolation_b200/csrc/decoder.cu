@@ -1,0 +1,303 @@
+// Fused 2-layer decoder of the hash-grid models (HashMLP: enc(K0) -> H -> 1, models.py:712-739 / nb cell 37).
+//
+// The layers are far too small for tensor-core tiles (K0 = L*F <= 64, H <= 64, one output), so the whole
+// decoder runs per coordinate in registers with the weights broadcast from shared memory:
+//   decoder2_fwd_kernel : y = act2(b2 + w2 . act1(W1 enc + b1)); only y and the scalar pre-activation of the
+//                         output layer are written (8 B/coord) - the hidden layer is recomputed in backward.
+//   decoder2_bwd_kernel : recompute hidden layer, dEnc = W1^T (dh * act1'), and the parameter gradients.
+//                         dW1 (H x K0, a reduction over the batch) is formed per 128-coordinate chunk from
+//                         shared-memory copies of dPre1 and enc, accumulated in registers across the
+//                         persistent block's chunks and flushed once per block with red.global.add.
+#include "common.cuh"
+
+namespace mri {
+namespace {
+
+constexpr int DEC_THREADS = 128;
+constexpr int DP_PAD = 4;  // dPre1 rows are H + 4 floats apart: conflict-free float4 stores, still 16-byte aligned
+
+template <int ACT>
+__device__ __forceinline__ void act_and_grad(float pre, float& a, float& g) {
+  if constexpr (ACT == MRI_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erff(pre * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * pre * pre);
+    a = pre * cdf;
+    g = cdf + pre * pdf;
+  } else if constexpr (ACT == MRI_ACT_RELU) {
+    a = fmaxf(pre, 0.0f);
+    g = pre > 0.0f ? 1.0f : 0.0f;
+  } else {
+    a = pre;
+    g = 1.0f;
+  }
+}
+
+// hidden pre-activations of one coordinate: h[j] = b1[j] + sum_k enc[k] W1[j][k]  (W1t = W1 transposed in smem)
+template <int K0, int H>
+__device__ __forceinline__ void hidden_pre(const float* __restrict__ enc_row, const float* __restrict__ w1t,
+                                           const float* __restrict__ b1s, float (&h)[H]) {
+#pragma unroll
+  for (int j = 0; j < H; ++j) h[j] = b1s[j];
+#pragma unroll 1
+  for (int k4 = 0; k4 < K0 / 4; ++k4) {
+    const float4 e4 = __ldg(reinterpret_cast<const float4*>(enc_row) + k4);
+    const float e[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* row = reinterpret_cast<const float4*>(w1t + (4 * k4 + u) * H);
+#pragma unroll
+      for (int q = 0; q < H / 4; ++q) {
+        const float4 w = row[q];
+        h[4 * q + 0] = fmaf(e[u], w.x, h[4 * q + 0]);
+        h[4 * q + 1] = fmaf(e[u], w.y, h[4 * q + 1]);
+        h[4 * q + 2] = fmaf(e[u], w.z, h[4 * q + 2]);
+        h[4 * q + 3] = fmaf(e[u], w.w, h[4 * q + 3]);
+      }
+    }
+  }
+}
+
+template <int K0, int H, int ACT1>
+__global__ void __launch_bounds__(DEC_THREADS) decoder2_fwd_kernel(const float* __restrict__ enc, int64_t n,
+                                                                    const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                    const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                    int act2, float* __restrict__ y, float* __restrict__ pre2_out) {
+  __shared__ __align__(16) float w1t[K0 * H];
+  __shared__ __align__(16) float b1s[H];
+  __shared__ __align__(16) float w2s[H];
+  for (int e = threadIdx.x; e < K0 * H; e += DEC_THREADS) {
+    const int j = e / K0, k = e - j * K0;
+    w1t[k * H + j] = __ldg(w1 + e);
+  }
+  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+    b1s[e] = __ldg(b1 + e);
+    w2s[e] = __ldg(w2 + e);
+  }
+  const float b2v = __ldg(b2);
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * DEC_THREADS;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * DEC_THREADS + threadIdx.x; i < n; i += stride) {
+    float h[H];
+    hidden_pre<K0, H>(enc + i * K0, w1t, b1s, h);
+    float pre2 = b2v;
+#pragma unroll
+    for (int j = 0; j < H; ++j) pre2 = fmaf(activate<ACT1>(h[j], 1.0f), w2s[j], pre2);
+    y[i] = activate_rt(act2, pre2, 1.0f);
+    if (pre2_out) pre2_out[i] = pre2;
+  }
+}
+
+template <int K0, int H, int ACT1>
+__global__ void __launch_bounds__(DEC_THREADS) decoder2_bwd_kernel(const float* __restrict__ enc, int64_t n,
+                                                                    const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                    const float* __restrict__ w2, const float* __restrict__ pre2,
+                                                                    const float* __restrict__ gy, int act2, float* __restrict__ denc,
+                                                                    float* __restrict__ gw1, float* __restrict__ gb1,
+                                                                    float* __restrict__ gw2, float* __restrict__ gb2) {
+  constexpr int JG = DEC_THREADS / K0;  // threads along the hidden axis in the dW1 phase
+  constexpr int JPT = H / JG;           // hidden units per thread in the dW1 phase
+  constexpr int DPS = H + DP_PAD;       // row stride of the per-coordinate staging arrays
+  static_assert(DEC_THREADS % K0 == 0 && H % JG == 0 && JPT % 4 == 0 && H <= DEC_THREADS, "unsupported decoder shape");
+  extern __shared__ __align__(16) float dsm[];
+  float* w1t = dsm;                        // [K0][H]    for the hidden-layer recompute
+  float* w1s = w1t + K0 * H;               // [H][K0]    for dEnc = W1^T dPre1
+  float* b1s = w1s + K0 * H;               // [H]
+  float* w2s = b1s + H;                    // [H]
+  float* dpre_s = w2s + H;                 // [128][H+4] dPre1 of the current chunk
+  float* adp_s = dpre_s + DEC_THREADS * DPS;  // [128][H+4] act1(pre1) * dPre2 of the current chunk (for dw2)
+  float* enc_t = adp_s + DEC_THREADS * DPS;   // [K0][129]  enc of the current chunk, transposed, padded
+  for (int e = threadIdx.x; e < K0 * H; e += DEC_THREADS) {
+    const float v = __ldg(w1 + e);
+    const int j = e / K0, k = e - j * K0;
+    w1s[e] = v;
+    w1t[k * H + j] = v;
+  }
+  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+    b1s[e] = __ldg(b1 + e);
+    w2s[e] = __ldg(w2 + e);
+  }
+  __syncthreads();
+
+  float acc_w1[JPT];
+#pragma unroll
+  for (int t = 0; t < JPT; ++t) acc_w1[t] = 0.0f;
+  float acc_b1 = 0.0f, acc_w2 = 0.0f, acc_b2 = 0.0f;  // column sums owned by threads < H (b2: every thread)
+  const int my_k = threadIdx.x % K0;
+  const int my_j0 = (threadIdx.x / K0) * JPT;
+
+  const int64_t chunks = (n + DEC_THREADS - 1) / DEC_THREADS;
+  for (int64_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const int64_t i = chunk * DEC_THREADS + threadIdx.x;
+    const bool live = i < n;
+    // ---- phase A: one coordinate per thread ----
+    {
+      float h[H];
+      float dp2 = 0.0f;
+      if (live) {
+        hidden_pre<K0, H>(enc + i * K0, w1t, b1s, h);
+        dp2 = __ldg(gy + i) * activate_grad_rt(act2, __ldg(pre2 + i), 1.0f);
+        acc_b2 += dp2;
+      } else {
+#pragma unroll
+        for (int j = 0; j < H; ++j) h[j] = 0.0f;
+      }
+      float4* dp_row = reinterpret_cast<float4*>(dpre_s + threadIdx.x * DPS);
+      float4* ad_row = reinterpret_cast<float4*>(adp_s + threadIdx.x * DPS);
+#pragma unroll
+      for (int q = 0; q < H / 4; ++q) {
+        float a[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          act_and_grad<ACT1>(h[4 * q + u], a[u], g[u]);
+          h[4 * q + u] = dp2 * w2s[4 * q + u] * g[u];  // dPre1
+          a[u] *= dp2;
+        }
+        dp_row[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        ad_row[q] = make_float4(a[0], a[1], a[2], a[3]);
+      }
+      // dEnc[k] = sum_j dPre1[j] W1[j][k], four k at a time; park enc (transposed) for the dW1 phase
+#pragma unroll 1
+      for (int q = 0; q < K0 / 4; ++q) {
+        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < H; ++j) {
+            const float4 w = reinterpret_cast<const float4*>(w1s + j * K0)[q];
+            acc.x = fmaf(h[j], w.x, acc.x); acc.y = fmaf(h[j], w.y, acc.y);
+            acc.z = fmaf(h[j], w.z, acc.z); acc.w = fmaf(h[j], w.w, acc.w);
+          }
+          reinterpret_cast<float4*>(denc + i * K0)[q] = acc;
+          e4 = __ldg(reinterpret_cast<const float4*>(enc + i * K0) + q);
+        }
+        enc_t[(4 * q + 0) * (DEC_THREADS + 1) + threadIdx.x] = e4.x;
+        enc_t[(4 * q + 1) * (DEC_THREADS + 1) + threadIdx.x] = e4.y;
+        enc_t[(4 * q + 2) * (DEC_THREADS + 1) + threadIdx.x] = e4.z;
+        enc_t[(4 * q + 3) * (DEC_THREADS + 1) + threadIdx.x] = e4.w;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: dW1[j][k] += sum_c dPre1[c][j] enc[c][k]; thread owns (k = my_k, j in [my_j0, +JPT)) ----
+#pragma unroll 2
+    for (int c = 0; c < DEC_THREADS; ++c) {
+      const float ek = enc_t[my_k * (DEC_THREADS + 1) + c];
+      const float4* dp = reinterpret_cast<const float4*>(dpre_s + c * DPS + my_j0);
+#pragma unroll
+      for (int q = 0; q < JPT / 4; ++q) {
+        const float4 d = dp[q];
+        acc_w1[4 * q + 0] = fmaf(d.x, ek, acc_w1[4 * q + 0]);
+        acc_w1[4 * q + 1] = fmaf(d.y, ek, acc_w1[4 * q + 1]);
+        acc_w1[4 * q + 2] = fmaf(d.z, ek, acc_w1[4 * q + 2]);
+        acc_w1[4 * q + 3] = fmaf(d.w, ek, acc_w1[4 * q + 3]);
+      }
+    }
+    // column sums: db1[j] += sum_c dPre1[c][j], dw2[j] += sum_c act1(pre1[c][j]) dPre2[c]
+    if (threadIdx.x < H) {
+#pragma unroll 8
+      for (int c = 0; c < DEC_THREADS; ++c) {
+        acc_b1 += dpre_s[c * DPS + threadIdx.x];
+        acc_w2 += adp_s[c * DPS + threadIdx.x];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: one round of atomics per block ----
+#pragma unroll
+  for (int t = 0; t < JPT; ++t) red_add_f32(gw1 + (my_j0 + t) * K0 + my_k, acc_w1[t]);
+  if (threadIdx.x < H) {
+    red_add_f32(gb1 + threadIdx.x, acc_b1);
+    red_add_f32(gw2 + threadIdx.x, acc_w2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc_b2 += __shfl_xor_sync(0xffffffffu, acc_b2, o);
+  if ((threadIdx.x & 31) == 0) red_add_f32(gb2, acc_b2);
+}
+
+template <int K0, int H>
+size_t bwd_smem_bytes() {
+  return sizeof(float) * (2 * K0 * H + 2 * H + 2 * DEC_THREADS * (H + DP_PAD) + K0 * (DEC_THREADS + 1));
+}
+
+template <int K0, int H, int ACT1>
+int launch_fwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* b2, int act2,
+               float* y, float* pre2, cudaStream_t s) {
+  int64_t blocks = (n + DEC_THREADS - 1) / DEC_THREADS;
+  const int64_t cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  decoder2_fwd_kernel<K0, H, ACT1><<<static_cast<int>(blocks), DEC_THREADS, 0, s>>>(enc, n, w1, b1, w2, b2, act2, y, pre2);
+  MRI_LAUNCH_OK("decoder2_fwd_kernel");
+  return MRI_OK;
+}
+
+template <int K0, int H, int ACT1>
+int launch_bwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* pre2,
+               const float* gy, int act2, float* denc, float* gw1, float* gb1, float* gw2, float* gb2, cudaStream_t s) {
+  const size_t smem = bwd_smem_bytes<K0, H>();
+  MRI_CUDA_OK(cudaFuncSetAttribute(decoder2_bwd_kernel<K0, H, ACT1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  int64_t blocks = (n + DEC_THREADS - 1) / DEC_THREADS;
+  const int64_t cap = 2LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  decoder2_bwd_kernel<K0, H, ACT1><<<static_cast<int>(blocks), DEC_THREADS, smem, s>>>(enc, n, w1, b1, w2, pre2, gy, act2,
+                                                                                        denc, gw1, gb1, gw2, gb2);
+  MRI_LAUNCH_OK("decoder2_bwd_kernel");
+  return MRI_OK;
+}
+
+bool shape_ok(int k0, int h) { return (k0 == 16 || k0 == 32 || k0 == 64) && (h == 32 || h == 64); }
+
+}  // namespace
+}  // namespace mri
+
+using namespace mri;
+
+#define MRI_DEC_DISPATCH(K0V, HV, ACTV, CALL)                                                   \
+  if (k0 == K0V && h == HV && act1 == ACTV) return CALL(K0V, HV, ACTV);
+#define MRI_DEC_ALL(CALL)                                                                        \
+  MRI_DEC_DISPATCH(16, 32, MRI_ACT_GELU, CALL) MRI_DEC_DISPATCH(16, 64, MRI_ACT_GELU, CALL)       \
+  MRI_DEC_DISPATCH(32, 32, MRI_ACT_GELU, CALL) MRI_DEC_DISPATCH(32, 64, MRI_ACT_GELU, CALL)       \
+  MRI_DEC_DISPATCH(64, 32, MRI_ACT_GELU, CALL) MRI_DEC_DISPATCH(64, 64, MRI_ACT_GELU, CALL)       \
+  MRI_DEC_DISPATCH(16, 32, MRI_ACT_RELU, CALL) MRI_DEC_DISPATCH(16, 64, MRI_ACT_RELU, CALL)       \
+  MRI_DEC_DISPATCH(32, 32, MRI_ACT_RELU, CALL) MRI_DEC_DISPATCH(32, 64, MRI_ACT_RELU, CALL)       \
+  MRI_DEC_DISPATCH(64, 32, MRI_ACT_RELU, CALL) MRI_DEC_DISPATCH(64, 64, MRI_ACT_RELU, CALL)
+
+extern "C" int mri_decoder2_supported(int k0, int h, int act1) {
+  return (shape_ok(k0, h) && (act1 == MRI_ACT_GELU || act1 == MRI_ACT_RELU)) ? 1 : 0;
+}
+
+extern "C" int mri_decoder2_forward(const float* enc, int64_t n, int k0, int h, const float* w1, const float* b1,
+                                    const float* w2, const float* b2, int act1, int act2, float* y, float* pre2,
+                                    void* stream) {
+  if (n < 0) return fail(MRI_ERR_INVALID, "decoder2_forward: negative n");
+  if (n == 0) return MRI_OK;
+  if (!enc || !w1 || !b1 || !w2 || !b2 || !y) return fail(MRI_ERR_INVALID, "decoder2_forward: null pointer");
+  if (!mri_decoder2_supported(k0, h, act1))
+    return fail(MRI_ERR_UNSUPPORTED, "decoder2_forward: no fused kernel for K0=%d H=%d act=%d", k0, h, act1);
+  if (reinterpret_cast<uintptr_t>(enc) & 15) return fail(MRI_ERR_INVALID, "decoder2_forward: enc must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(K0V, HV, ACTV) launch_fwd<K0V, HV, ACTV>(enc, n, w1, b1, w2, b2, act2, y, pre2, s)
+  MRI_DEC_ALL(CALL)
+#undef CALL
+  return fail(MRI_ERR_UNSUPPORTED, "decoder2_forward: dispatch miss");
+}
+
+extern "C" int mri_decoder2_backward(const float* enc, int64_t n, int k0, int h, const float* w1, const float* b1,
+                                     const float* w2, const float* pre2, const float* grad_y, int act1, int act2,
+                                     float* grad_enc, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
+                                     void* stream) {
+  if (n < 0) return fail(MRI_ERR_INVALID, "decoder2_backward: negative n");
+  if (n == 0) return MRI_OK;
+  if (!enc || !w1 || !b1 || !w2 || !pre2 || !grad_y || !grad_enc || !grad_w1 || !grad_b1 || !grad_w2 || !grad_b2)
+    return fail(MRI_ERR_INVALID, "decoder2_backward: null pointer");
+  if (!mri_decoder2_supported(k0, h, act1))
+    return fail(MRI_ERR_UNSUPPORTED, "decoder2_backward: no fused kernel for K0=%d H=%d act=%d", k0, h, act1);
+  if ((reinterpret_cast<uintptr_t>(enc) | reinterpret_cast<uintptr_t>(grad_enc)) & 15)
+    return fail(MRI_ERR_INVALID, "decoder2_backward: enc/grad_enc must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(K0V, HV, ACTV) \
+  launch_bwd<K0V, HV, ACTV>(enc, n, w1, b1, w2, pre2, grad_y, act2, grad_enc, grad_w1, grad_b1, grad_w2, grad_b2, s)
+  MRI_DEC_ALL(CALL)
+#undef CALL
+  return fail(MRI_ERR_UNSUPPORTED, "decoder2_backward: dispatch miss");
+}

@@ -176,6 +176,49 @@ def dense(x, weight, bias=None, act="identity", w0: float = 1.0):
     return DenseFn.apply(x, weight, bias, activation_code(act), float(w0))
 
 
+class Decoder2Fn(torch.autograd.Function):
+    """Fused 2-layer decoder enc -> H -> 1 (csrc/decoder.cu): HashMLP's decoder blocks without BatchNorm."""
+
+    @staticmethod
+    def forward(ctx, enc, w1, b1, w2, b2, act1: int, act2: int):
+        _lib.require_cuda_f32(enc, "decoder input")
+        h, k0 = w1.shape
+        e2 = enc.reshape(-1, k0).contiguous()
+        n = e2.shape[0]
+        y = torch.empty((n, 1), device=enc.device, dtype=torch.float32)
+        needs_grad = enc.requires_grad or w1.requires_grad
+        pre2 = torch.empty((n,), device=enc.device, dtype=torch.float32) if needs_grad else None
+        _lib.call("mri_decoder2_forward", e2.data_ptr(), n, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                  b2.data_ptr(), act1, act2, y.data_ptr(), _lib.ptr(pre2), _lib.stream())
+        ctx.acts = (act1, act2)
+        ctx.params = (w1, b1, w2, b2)
+        ctx.save_for_backward(e2, pre2)
+        ctx.enc_shape = enc.shape
+        return y.reshape(*enc.shape[:-1], 1)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        e2, pre2 = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.params
+        h, k0 = w1.shape
+        n = e2.shape[0]
+        gy = grad_y.reshape(n).contiguous()
+        genc = torch.empty_like(e2)
+        grads, ret = [], []
+        for p in (w1, b1, w2, b2):
+            d = _direct_grad(p)
+            grads.append(d if d is not None else torch.zeros_like(p))
+            ret.append(None if d is not None else grads[-1])
+        _lib.call("mri_decoder2_backward", e2.data_ptr(), n, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                  pre2.data_ptr(), gy.data_ptr(), ctx.acts[0], ctx.acts[1], genc.data_ptr(), grads[0].data_ptr(),
+                  grads[1].data_ptr(), grads[2].data_ptr(), grads[3].data_ptr(), _lib.stream())
+        return (genc.reshape(ctx.enc_shape), ret[0], ret[1], ret[2], ret[3], None, None)
+
+
+def decoder2_supported(k0: int, h: int, act1: int) -> bool:
+    return bool(_lib.lib().mri_decoder2_supported(int(k0), int(h), int(act1)))
+
+
 # ---------------------------------------------------------------------------------- loss
 class MseFn(torch.autograd.Function):
     """F.mse_loss(y, y_pred) (models.py:64) with the gradient produced in the same pass.

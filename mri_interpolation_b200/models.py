@@ -339,7 +339,30 @@ class HashMLP(BaseMLP):
             x = m(x)
         return x
 
+    def _fused_decoder_plan(self):
+        """(lin1, lin2, act1, act2) when the decoder is two Linear+activation blocks that csrc/decoder.cu fuses."""
+        plan = self.__dict__.get("_decoder_plan", 0)
+        if plan != 0:
+            return plan
+        plan = None
+        if len(self.decoder) == 2:
+            blocks = [list(b) for b in self.decoder]
+            ok = all(len(b) >= 2 and isinstance(b[0], nn.Linear) and b[0].bias is not None and
+                     _fusable_activation(b[1]) is not None and
+                     all(isinstance(m, nn.Dropout) and m.p == 0.0 for m in b[2:]) for b in blocks)
+            if ok:
+                l1, l2 = blocks[0][0], blocks[1][0]
+                a1, a2 = _fusable_activation(blocks[0][1]), _fusable_activation(blocks[1][1])
+                if l2.out_features == 1 and Fn.decoder2_supported(l1.in_features, l1.out_features, a1):
+                    plan = (l1, l2, a1, a2)
+        self.__dict__["_decoder_plan"] = plan
+        return plan
+
     def decode(self, z):
+        plan = self._fused_decoder_plan() if z.is_cuda else None
+        if plan is not None:
+            l1, l2, a1, a2 = plan
+            return Fn.Decoder2Fn.apply(z, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
         for block in self.decoder:
             z = self._run_block(block, z)
         return z

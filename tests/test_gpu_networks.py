@@ -202,3 +202,26 @@ def test_training_steps_track_the_oracle():
     sd = net.state_dict()
     for k, v in ref.items():
         assert rel_err(sd[k], v.detach()) < 1e-4, k
+
+
+@pytest.mark.parametrize("k0,h,act", [(32, 64, "gelu"), (16, 64, "gelu"), (64, 32, "relu"), (16, 32, "relu"), (32, 32, "gelu")])
+@pytest.mark.parametrize("n", [1, 127, 1000, 40000])
+def test_fused_decoder2_vs_torch(k0, h, act, n):
+    from mri_interpolation_b200 import functional as Fn
+    gen = torch.Generator().manual_seed(k0 + h + n)
+    f = {"gelu": F.gelu, "relu": F.relu}[act]
+    enc = (torch.randn(n, k0, generator=gen)).requires_grad_()
+    l1, l2 = torch.nn.Linear(k0, h), torch.nn.Linear(h, 1)
+    y_ref = f(l2(f(l1(enc))))
+    gy = torch.randn(n, 1, generator=gen)
+    y_ref.backward(gy)
+    code = Fn.activation_code(act)
+    encd = enc.detach().to(DEV).requires_grad_()
+    ps = [p.detach().to(DEV).requires_grad_() for p in (l1.weight, l1.bias, l2.weight, l2.bias)]
+    assert Fn.decoder2_supported(k0, h, code)
+    y = Fn.Decoder2Fn.apply(encd, *ps, code, code)
+    assert rel_err(y, y_ref) < 1e-5
+    y.backward(gy.to(DEV))
+    assert rel_err(encd.grad, enc.grad) < 1e-4
+    for p, r in zip(ps, (l1.weight, l1.bias, l2.weight, l2.bias)):
+        assert rel_err(p.grad, r.grad) < 1e-4
