@@ -43,8 +43,8 @@ HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch-log2", type=int, default=19)
     ap.add_argument("--cpu-batch-log2", type=int, default=15)
@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -214,11 +214,12 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(1337 + rank)
     total_steps = args.steps + args.warmup
-    # the epoch's shuffled index stream is drawn up front (like a DataLoader sampler); slicing it is free
-    index = torch.randint(0, sampler.total, (total_steps, n), device=dev, generator=gen)
+    # the shuffled index stream is drawn up front (like a DataLoader sampler), as a ring of 32 batches
+    ring = 32
+    index = torch.randint(0, sampler.total, (ring, n), device=dev, generator=gen)
 
     def step(i):
-        x, y = sampler.batch(index[i])
+        x, y = sampler.batch(index[i % ring])
         loss = model.training_step((x, y), i)
         loss.backward()
         opt.step()
@@ -252,7 +253,7 @@ def main():
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = n * world / (ms_step * 1e-3)
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- e2e: host batches through the public API
     host_x = torch.empty((n, 4), dtype=torch.float32).pin_memory()

@@ -1,8 +1,8 @@
 // Multiresolution hash-grid encoding kernels for sm_100a (B200).
 //
-//   hashgrid_fwd_kernel   K1: all corners of one (coordinate, level) per thread, gathers issued
-//                         back-to-back (2^D independent LDG.64/128 in flight per thread), no
-//                         intermediates in memory.  grid = (ceil(n/256), L): blocks are scheduled
+//   hashgrid_fwd_kernel   K1: two lanes per (coordinate, level), each walking half of the 2^D corners with
+//                         its gathers issued back-to-back (2^(D-1) independent LDG.64/128 in flight per
+//                         thread), no intermediates in memory.  grid = (ceil(n/128), L): blocks are scheduled
 //                         level-major so one level's table is the L2/L1 working set at a time.
 //   hashgrid_bwd_kernel   K2: recomputes hashes/weights and scatters w*dOut with vector
 //                         reductions red.global.add.v2/v4.f32 (SASS REDG.E.ADD.F32x2/x4).
@@ -64,21 +64,34 @@ __device__ __forceinline__ void store_feat(float* dst, const Feat<F>& a) {
   }
 }
 
+// ---- "pair-lane" mapping -----------------------------------------------------------------------
+// Two adjacent lanes share one (coordinate, level): lane bit 0 selects the lower/upper cell index on axis 0
+// (PRIME[0] = 1), each lane walks the 2^(D-1) corners of the remaining axes.  The two corners of an axis-0
+// pair hash to rows h and h' = h ^ (x0 ^ (x0+1)); for x0 % 4 != 3 they fall into the same 32-byte sector
+// (F = 2: 8-byte rows), and because they now sit in neighbouring lanes of the SAME load/red instruction the
+// LSU merges them into one L1 wavefront / one L2 request: ~10 instead of 16 sectors per (coordinate, level).
 template <int D, int F, bool POW2>
-__device__ __forceinline__ Feat<F> encode_one_level(const Cell<D>& cell, const LevelDev& lv, const float* __restrict__ tbl) {
-  constexpr int C = 1 << D;
-  Feat<F> rows[C];
+__device__ __forceinline__ Feat<F> encode_half_level(const Cell<D>& cell, int b0, const LevelDev& lv,
+                                                     const float* __restrict__ tbl) {
+  constexpr int CH = 1 << (D - 1);
+  const uint32_t t0 = cell.lo[0] + static_cast<uint32_t>(b0);
+  const float w0 = b0 ? cell.wu[0] : cell.wl[0];
+  Feat<F> rows[CH];
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const uint32_t h = wrap_rows<POW2>(corner_hash<D>(cell, c), lv);
-    rows[c] = gather_row<F>(tbl + static_cast<size_t>(h) * F);
+  for (int c = 0; c < CH; ++c) {
+    uint32_t h = t0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) h ^= ((c >> (d - 1)) & 1) ? (cell.lo[d] + prime(d)) : cell.lo[d];
+    rows[c] = gather_row<F>(tbl + static_cast<size_t>(wrap_rows<POW2>(h, lv)) * F);
   }
   Feat<F> acc;
 #pragma unroll
   for (int f = 0; f < F; ++f) acc.v[f] = 0.0f;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {  // ascending corner order, like torch.sum over dim=-2
-    const float w = corner_weight<D>(cell, c);
+  for (int c = 0; c < CH; ++c) {
+    float w = w0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) w = __fmul_rn(w, ((c >> (d - 1)) & 1) ? cell.wu[d] : cell.wl[d]);
 #pragma unroll
     for (int f = 0; f < F; ++f) acc.v[f] = fmaf(rows[c].v[f], w, acc.v[f]);
   }
@@ -90,24 +103,46 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const float* __restri
                                                            const __grid_constant__ LevelTable T, int64_t n,
                                                            int out_stride, float* __restrict__ out) {
   const int level = blockIdx.y;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 128 + (threadIdx.x >> 1);
+  const int b0 = threadIdx.x & 1;
+  const bool live = i < n;
   const LevelDev& lv = T.lv[level];
   float xv[D];
-  load_coord<D>(x, i, xv);
+  load_coord<D>(x, live ? i : 0, xv);
   const Cell<D> cell = make_cell<D>(xv, lv);
   const float* __restrict__ tbl = tables + lv.offset;
-  const Feat<F> acc = lv.is_pow2 ? encode_one_level<D, F, true>(cell, lv, tbl) : encode_one_level<D, F, false>(cell, lv, tbl);
-  store_feat<F>(out + i * out_stride + level * F, acc);
+  Feat<F> acc = lv.is_pow2 ? encode_half_level<D, F, true>(cell, b0, lv, tbl) : encode_half_level<D, F, false>(cell, b0, lv, tbl);
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc.v[f] += __shfl_xor_sync(0xffffffffu, acc.v[f], 1);
+  if (live && b0 == 0) store_feat<F>(out + i * out_stride + level * F, acc);
+}
+
+template <int D, int F, bool POW2>
+__device__ __forceinline__ void scatter_half_level(const Cell<D>& cell, int b0, const LevelDev& lv, float* tbl, const Feat<F>& g) {
+  constexpr int CH = 1 << (D - 1);
+  const uint32_t t0 = cell.lo[0] + static_cast<uint32_t>(b0);
+  const float w0 = b0 ? cell.wu[0] : cell.wl[0];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    uint32_t h = t0;
+    float w = w0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const bool up = (c >> (d - 1)) & 1;
+      h ^= up ? (cell.lo[d] + prime(d)) : cell.lo[d];
+      w = __fmul_rn(w, up ? cell.wu[d] : cell.wl[d]);
+    }
+    scatter_row<F>(tbl + static_cast<size_t>(wrap_rows<POW2>(h, lv)) * F, g, w);
+  }
 }
 
 template <int D, int F>
 __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grad_out,
                                                            const __grid_constant__ LevelTable T, int64_t n,
                                                            int out_stride, float* __restrict__ grad_tables) {
-  constexpr int C = 1 << D;
   const int level = blockIdx.y;
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 128 + (threadIdx.x >> 1);
+  const int b0 = threadIdx.x & 1;
   if (i >= n) return;
   const LevelDev& lv = T.lv[level];
   float xv[D];
@@ -115,19 +150,8 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const float* __restri
   const Cell<D> cell = make_cell<D>(xv, lv);
   float* tbl = grad_tables + lv.offset;
   const Feat<F> g = gather_row<F>(grad_out + i * out_stride + level * F);
-  if (lv.is_pow2) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const uint32_t h = wrap_rows<true>(corner_hash<D>(cell, c), lv);
-      scatter_row<F>(tbl + static_cast<size_t>(h) * F, g, corner_weight<D>(cell, c));
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const uint32_t h = wrap_rows<false>(corner_hash<D>(cell, c), lv);
-      scatter_row<F>(tbl + static_cast<size_t>(h) * F, g, corner_weight<D>(cell, c));
-    }
-  }
+  if (lv.is_pow2) scatter_half_level<D, F, true>(cell, b0, lv, tbl, g);
+  else scatter_half_level<D, F, false>(cell, b0, lv, tbl, g);
 }
 
 template <int D>
@@ -154,7 +178,7 @@ __global__ void __launch_bounds__(256) hashgrid_corners_kernel(const float* __re
 template <int D, int F>
 int launch_fwd(const float* x, const float* tables, const LevelTable& T, int64_t n, int n_levels, float* out,
                cudaStream_t s) {
-  dim3 grid(static_cast<unsigned>((n + 255) / 256), n_levels);
+  dim3 grid(static_cast<unsigned>((n + 127) / 128), n_levels);  // 2 lanes per coordinate
   hashgrid_fwd_kernel<D, F><<<grid, 256, 0, s>>>(x, tables, T, n, n_levels * F, out);
   MRI_LAUNCH_OK("hashgrid_fwd_kernel");
   return MRI_OK;
@@ -162,7 +186,7 @@ int launch_fwd(const float* x, const float* tables, const LevelTable& T, int64_t
 template <int D, int F>
 int launch_bwd(const float* x, const float* go, const LevelTable& T, int64_t n, int n_levels, float* gt,
                cudaStream_t s) {
-  dim3 grid(static_cast<unsigned>((n + 255) / 256), n_levels);
+  dim3 grid(static_cast<unsigned>((n + 127) / 128), n_levels);  // 2 lanes per coordinate
   hashgrid_bwd_kernel<D, F><<<grid, 256, 0, s>>>(x, go, T, n, n_levels * F, gt);
   MRI_LAUNCH_OK("hashgrid_bwd_kernel");
   return MRI_OK;
