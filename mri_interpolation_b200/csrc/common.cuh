@@ -109,11 +109,29 @@ __device__ __forceinline__ void load_coord(const float* __restrict__ x, int64_t 
   }
 }
 
-// exact GELU (nn.GELU default, approximate='none') and its derivative
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf-GELU (nn.GELU default, approximate='none') and its derivative.  Phi(x) = 0.5 (1 + erf(x/sqrt2)) is
+// evaluated with the Abramowitz-Stegun 7.1.26 rational form (|abs err| <= 1.5e-7, far inside the 1e-3 parity
+// bound): one MUFU.RCP + one MUFU.EX2 + 5 FMA, and exp(-x^2/2) is shared with the Gaussian pdf of the derivative.
+__device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-0.5f * x * x);  // = exp(-z^2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_erfc = 0.5f * poly * t * e;  // 0.5 * erfc(z)
+  cdf = x >= 0.0f ? 1.0f - half_erfc : half_erfc;
+  pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
+  return x * cdf;
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  float cdf, pdf;
+  gelu_cdf_pdf(x, cdf, pdf);
   return cdf + x * pdf;
 }
 

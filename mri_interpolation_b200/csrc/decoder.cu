@@ -19,8 +19,8 @@ constexpr int DP_PAD = 4;  // dPre1 rows are H + 4 floats apart: conflict-free f
 template <int ACT>
 __device__ __forceinline__ void act_and_grad(float pre, float& a, float& g) {
   if constexpr (ACT == MRI_ACT_GELU) {
-    const float cdf = 0.5f * (1.0f + erff(pre * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * __expf(-0.5f * pre * pre);
+    float cdf, pdf;
+    gelu_cdf_pdf(pre, cdf, pdf);
     a = pre * cdf;
     g = cdf + pre * pdf;
   } else if constexpr (ACT == MRI_ACT_RELU) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void hidden_pre(const float* __restrict__ enc_row, co
 }
 
 template <int K0, int H, int ACT1>
-__global__ void __launch_bounds__(DEC_THREADS) decoder2_fwd_kernel(const float* __restrict__ enc, int64_t n,
+__global__ void __launch_bounds__(DEC_THREADS, 3) decoder2_fwd_kernel(const float* __restrict__ enc, int64_t n,
                                                                     const float* __restrict__ w1, const float* __restrict__ b1,
                                                                     const float* __restrict__ w2, const float* __restrict__ b2,
                                                                     int act2, float* __restrict__ y, float* __restrict__ pre2_out) {
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decoder2_fwd_kernel(const float* 
 }
 
 template <int K0, int H, int ACT1>
-__global__ void __launch_bounds__(DEC_THREADS) decoder2_bwd_kernel(const float* __restrict__ enc, int64_t n,
+__global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const float* __restrict__ enc, int64_t n,
                                                                     const float* __restrict__ w1, const float* __restrict__ b1,
                                                                     const float* __restrict__ w2, const float* __restrict__ pre2,
                                                                     const float* __restrict__ gy, int act2, float* __restrict__ denc,

@@ -79,6 +79,61 @@ class DeviceBatchLoader:
         self.epoch += 1
 
 
+class PrefetchLoader:
+    """Wraps an iterable of HOST batches (ideally pinned) and yields DEVICE batches: the H2D copy of batch
+    i+1 runs on a side stream while batch i is being consumed (double buffering, no per-step allocation)."""
+
+    def __init__(self, host_batches, device, depth: int = 2):
+        self.host_batches = host_batches
+        self.device = torch.device(device)
+        self.depth = max(2, depth)
+        self.copy_stream = torch.cuda.Stream(self.device)
+
+    def __len__(self):
+        return len(self.host_batches)
+
+    def __iter__(self):
+        main = torch.cuda.current_stream(self.device)
+        slots = [None] * self.depth
+        ready = [torch.cuda.Event() for _ in range(self.depth)]
+        freed = [torch.cuda.Event() for _ in range(self.depth)]
+        it = iter(self.host_batches)
+
+        def issue(slot):
+            try:
+                batch = next(it)
+            except StopIteration:
+                return False
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(freed[slot])
+                if slots[slot] is None:
+                    slots[slot] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch)
+                for dst, src in zip(slots[slot], batch):
+                    if dst.shape != src.shape:
+                        slots[slot] = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in batch)
+                        break
+                for dst, src in zip(slots[slot], batch):
+                    dst.copy_(src, non_blocking=True)
+                ready[slot].record(self.copy_stream)
+            return True
+
+        for s in range(self.depth):
+            freed[s].record(main)
+        pending = []
+        for s in range(self.depth - 1):
+            if issue(s):
+                pending.append(s)
+        nxt = self.depth - 1
+        while pending:
+            cur = pending.pop(0)
+            main.wait_event(ready[cur])
+            if issue(nxt):
+                pending.append(nxt)
+                nxt = (nxt + 1) % self.depth
+            yield slots[cur]
+            freed[cur].record(main)
+
+
 class MriImage(Dataset):
     """Coordinates in ``coords`` (M, D), intensities in ``pixels`` (M, 1) (datamodules.py:123-172)."""
 

@@ -148,3 +148,16 @@ def test_voxel_sampler_matches_mriimage_semantics():
     s = Fn.VoxelSampler(pixels.to(DEV), shape)
     x, y = s.batch(idx.to(DEV))
     assert torch.equal(x.cpu(), coords[idx]) and torch.equal(y.cpu(), pixels[idx])
+
+
+def test_prefetch_loader_yields_host_batches_in_order():
+    from mri_interpolation_b200.datamodules import PrefetchLoader
+    gen = torch.Generator().manual_seed(8)
+    host = [(torch.rand(1000 + 10 * i, 4, generator=gen).pin_memory(), torch.rand(1000 + 10 * i, 1, generator=gen).pin_memory())
+            for i in range(7)]
+    seen = []
+    for x, y in PrefetchLoader(host, DEV):
+        seen.append((x.clone(), y.clone()))  # slots are recycled: consume before asking for the next batch
+    assert len(seen) == 7
+    for (x, y), (hx, hy) in zip(seen, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
