@@ -85,7 +85,7 @@ class FusedAdam(torch.optim.Optimizer):
     """
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 process_group=None, grad_average: bool = True, fuse_zero_grad: bool = True):
+                 process_group=None, grad_average: bool = True, fuse_zero_grad: bool = True, data_parallel: bool = True):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
@@ -96,6 +96,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(self.arena.data)
         self.step_count = 0
         self.process_group = process_group
+        self.data_parallel = data_parallel  # False: never all-reduce, even when torch.distributed is initialised
         self.grad_average = grad_average
         self.fuse_zero_grad = fuse_zero_grad
         self._grads_clean = True  # freshly allocated arena gradient is zero
@@ -103,7 +104,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     # -- distributed
     def _world(self) -> int:
-        if dist.is_available() and dist.is_initialized():
+        if self.data_parallel and dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self.process_group)
         return 1
 
