@@ -73,6 +73,12 @@ int mri_hashgrid_backward(const float* x, int64_t n, int dim, const float* grad_
                           float* grad_tables, const mri_level_t* host_levels, int n_levels,
                           int n_features, void* stream);
 
+/* Same, restricted to levels [level_begin, level_begin + level_count): lets the caller launch the backward
+ * in level groups and start the data-parallel all-reduce of a finished group while the next one runs. */
+int mri_hashgrid_backward_levels(const float* x, int64_t n, int dim, const float* grad_out,
+                                 float* grad_tables, const mri_level_t* host_levels, int n_levels,
+                                 int n_features, int level_begin, int level_count, void* stream);
+
 /* Parity probe: corner hashes (n, L, 2^dim) uint32 and weights (n, L, 2^dim) f32 in the
  * reference's corner order (encoding.py:69-78, 101-106, 121-124). Either output may be NULL. */
 int mri_hashgrid_corners(const float* x, int64_t n, int dim, const mri_level_t* host_levels,

@@ -44,6 +44,7 @@ _D = ctypes.c_double
 SIGNATURES = {
     "mri_hashgrid_forward": [_P, _I64, _I, _P, ctypes.POINTER(Level), _I, _I, _P, _P],
     "mri_hashgrid_backward": [_P, _I64, _I, _P, _P, ctypes.POINTER(Level), _I, _I, _P],
+    "mri_hashgrid_backward_levels": [_P, _I64, _I, _P, _P, ctypes.POINTER(Level), _I, _I, _I, _I, _P],
     "mri_hashgrid_corners": [_P, _I64, _I, ctypes.POINTER(Level), _I, _P, _P, _P],
     "mri_dense_forward": [_P, _I64, _P, _P, _I64, _I, _I, _I, _F, _P, _P, _P],
     "mri_dense_backward": [_P, _I64, _P, _P, _P, _I64, _I, _I, _I, _F, _P, _P, _P, _P, _P],

@@ -139,8 +139,8 @@ __device__ __forceinline__ void scatter_half_level(const Cell<D>& cell, int b0, 
 template <int D, int F>
 __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grad_out,
                                                            const __grid_constant__ LevelTable T, int64_t n,
-                                                           int out_stride, float* __restrict__ grad_tables) {
-  const int level = blockIdx.y;
+                                                           int out_stride, int level_begin, float* __restrict__ grad_tables) {
+  const int level = blockIdx.y + level_begin;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 128 + (threadIdx.x >> 1);
   const int b0 = threadIdx.x & 1;
   if (i >= n) return;
@@ -184,10 +184,10 @@ int launch_fwd(const float* x, const float* tables, const LevelTable& T, int64_t
   return MRI_OK;
 }
 template <int D, int F>
-int launch_bwd(const float* x, const float* go, const LevelTable& T, int64_t n, int n_levels, float* gt,
-               cudaStream_t s) {
-  dim3 grid(static_cast<unsigned>((n + 127) / 128), n_levels);  // 2 lanes per coordinate
-  hashgrid_bwd_kernel<D, F><<<grid, 256, 0, s>>>(x, go, T, n, n_levels * F, gt);
+int launch_bwd(const float* x, const float* go, const LevelTable& T, int64_t n, int n_levels, int level_begin,
+               int level_count, float* gt, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((n + 127) / 128), level_count);  // 2 lanes per coordinate
+  hashgrid_bwd_kernel<D, F><<<grid, 256, 0, s>>>(x, go, T, n, n_levels * F, level_begin, gt);
   MRI_LAUNCH_OK("hashgrid_bwd_kernel");
   return MRI_OK;
 }
@@ -266,10 +266,14 @@ extern "C" int mri_hashgrid_forward(const float* x, int64_t n, int dim, const fl
 #undef CALL
 }
 
-extern "C" int mri_hashgrid_backward(const float* x, int64_t n, int dim, const float* grad_out, float* grad_tables,
-                                     const mri_level_t* host_levels, int n_levels, int n_features, void* stream) {
+extern "C" int mri_hashgrid_backward_levels(const float* x, int64_t n, int dim, const float* grad_out, float* grad_tables,
+                                            const mri_level_t* host_levels, int n_levels, int n_features, int level_begin,
+                                            int level_count, void* stream) {
   int st = check_common(x, n, dim, host_levels, n_levels, n_features);
   if (st != MRI_OK) return st;
+  if (level_begin < 0 || level_count < 0 || level_begin + level_count > n_levels)
+    return fail(MRI_ERR_INVALID, "hashgrid_backward: level range [%d, +%d) outside 0..%d", level_begin, level_count, n_levels);
+  if (level_count == 0) return MRI_OK;
   if (n == 0) return MRI_OK;
   if (!grad_out || !grad_tables) return fail(MRI_ERR_INVALID, "hashgrid_backward: null grad pointer");
   if ((reinterpret_cast<uintptr_t>(grad_tables) & 15) || (reinterpret_cast<uintptr_t>(grad_out) & 15))
@@ -282,9 +286,14 @@ extern "C" int mri_hashgrid_backward(const float* x, int64_t n, int dim, const f
   st = make_level_table(host_levels, n_levels, dim, &T);
   if (st != MRI_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define CALL(D, F) launch_bwd<D, F>(x, grad_out, T, n, n_levels, grad_tables, s)
+#define CALL(D, F) launch_bwd<D, F>(x, grad_out, T, n, n_levels, level_begin, level_count, grad_tables, s)
   MRI_DISPATCH_DF(dim, n_features, CALL)
 #undef CALL
+}
+
+extern "C" int mri_hashgrid_backward(const float* x, int64_t n, int dim, const float* grad_out, float* grad_tables,
+                                     const mri_level_t* host_levels, int n_levels, int n_features, void* stream) {
+  return mri_hashgrid_backward_levels(x, n, dim, grad_out, grad_tables, host_levels, n_levels, n_features, 0, n_levels, stream);
 }
 
 extern "C" int mri_hashgrid_corners(const float* x, int64_t n, int dim, const mri_level_t* host_levels, int n_levels,

@@ -103,8 +103,18 @@ class HashGridFn(torch.autograd.Function):
                 off += s
             ret = tuple(targets)
         grid._bwd_layout.refresh(targets, grid._resolutions, grid._rows)
-        _lib.call("mri_hashgrid_backward", x2.data_ptr(), x2.shape[0], dim, go.data_ptr(), grid._bwd_layout.base,
-                  grid._bwd_layout.levels, n_levels, nf, _lib.stream())
+        hook = getattr(grid, "_grad_group_hook", None)
+        groups = getattr(grid, "_grad_groups", None)
+        if hook is not None and groups and all(d is not None for d in direct):
+            # level groups: the optimiser all-reduces a finished group while the next group's scatter runs
+            hook(-1)
+            for gi, (lo, hi) in enumerate(groups):
+                _lib.call("mri_hashgrid_backward_levels", x2.data_ptr(), x2.shape[0], dim, go.data_ptr(),
+                          grid._bwd_layout.base, grid._bwd_layout.levels, n_levels, nf, lo, hi - lo, _lib.stream())
+                hook(gi)
+        else:
+            _lib.call("mri_hashgrid_backward", x2.data_ptr(), x2.shape[0], dim, go.data_ptr(), grid._bwd_layout.base,
+                      grid._bwd_layout.levels, n_levels, nf, _lib.stream())
         return (None, None) + ret
 
 

@@ -101,6 +101,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.fuse_zero_grad = fuse_zero_grad
         self._grads_clean = True  # freshly allocated arena gradient is zero
         self.allreduce_count = 0
+        self._overlap = None
 
     # -- distributed
     def _world(self) -> int:
@@ -110,11 +111,64 @@ class FusedAdam(torch.optim.Optimizer):
 
     def sync_gradients(self) -> float:
         """Sum the flat gradient over the data-parallel ranks; returns the scale Adam must apply."""
-        if self._world() == 1:
+        world = self._world()
+        if world == 1:
             return 1.0
+        if self._overlap is not None and self._overlap["fired"]:
+            ov = self._overlap
+            if ov["fired"] != len(ov["groups"]) + 1:
+                raise MriB200Error("overlapped all-reduce: exactly one backward per optimiser step is required "
+                                   "(use overlap=False with gradient accumulation)")
+            for work in ov["pending"]:
+                work.wait()  # current stream waits for the bucket's all-reduce
+            ov["pending"], ov["fired"] = [], 0
+            self.allreduce_count += 1
+            return (1.0 / world) if self.grad_average else 1.0
         inv_world = allreduce_sum_(self.arena.grad, self.process_group)
         self.allreduce_count += 1
         return inv_world if self.grad_average else 1.0
+
+    # -- overlap of the gradient all-reduce with the hash-grid backward (SURVEY 5, option 2)
+    def enable_overlap(self, encoder, n_groups: int = 4) -> bool:
+        """Bucket the table gradients per level group: group g's all-reduce runs on a side stream while the
+        scatter kernel of group g+1 executes; the (small) non-table gradients go first.  Requires exactly one
+        backward per step.  Returns False (and stays on the single all-reduce) when not applicable."""
+        if self._world() == 1:
+            return False
+        tables = encoder.tables()
+        index = {id(p): i for i, p in enumerate(self.arena.params)}
+        if any(id(t) not in index for t in tables):
+            return False
+        pos = [index[id(t)] for t in tables]
+        if pos != list(range(pos[0], pos[0] + len(pos))):
+            return False  # tables are not consecutive in the arena
+        n_levels = len(tables)
+        n_groups = max(1, min(n_groups, n_levels))
+        bounds = [round(g * n_levels / n_groups) for g in range(n_groups + 1)]
+        groups = [(bounds[g], bounds[g + 1]) for g in range(n_groups) if bounds[g + 1] > bounds[g]]
+        offs = self.arena.offsets + [self.arena.numel]
+        slices = [(offs[pos[lo]], offs[pos[hi - 1] + 1]) for lo, hi in groups]
+        t_begin, t_end = offs[pos[0]], offs[pos[-1] + 1]
+        rest = [(0, t_begin), (t_end, self.arena.numel)]
+        self._overlap = {"groups": groups, "slices": slices, "rest": [r for r in rest if r[1] > r[0]], "pending": [],
+                         "fired": 0, "stream": torch.cuda.Stream(self.arena.grad.device)}
+        object.__setattr__(encoder, "_grad_groups", groups)
+        object.__setattr__(encoder, "_grad_group_hook", self._on_group_ready)
+        return True
+
+    def _on_group_ready(self, gi: int) -> None:
+        ov = self._overlap
+        if gi == -1 and ov["fired"] != 0:
+            raise MriB200Error("overlapped all-reduce: a second backward ran before optimizer.step()")
+        spans = ov["rest"] if gi == -1 else [ov["slices"][gi]]
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(ov["stream"]):
+            ov["stream"].wait_event(ready)
+            for a, b in spans:
+                ov["pending"].append(dist.all_reduce(self.arena.grad[a:b], op=dist.ReduceOp.SUM, group=self.process_group,
+                                                     async_op=True))
+        ov["fired"] += 1
 
     @torch.no_grad()
     def step(self, closure=None):
