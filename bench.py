@@ -303,6 +303,7 @@ def main():
 
     # ---- isolated kernel timings for the roofline (rank 0, L2 flushed between launches)
     roof, kern, infer = None, None, None
+    opt.disable_overlap(model.encoder)
     opt.data_parallel = False  # the isolated-kernel section below runs on rank 0 only: no collectives in it
     if rank == 0:
         peak, peak_src = peaks()

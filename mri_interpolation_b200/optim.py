@@ -156,6 +156,14 @@ class FusedAdam(torch.optim.Optimizer):
         object.__setattr__(encoder, "_grad_group_hook", self._on_group_ready)
         return True
 
+    def disable_overlap(self, encoder) -> None:
+        if self._overlap is not None:
+            for work in self._overlap["pending"]:
+                work.wait()
+        self._overlap = None
+        object.__setattr__(encoder, "_grad_groups", None)
+        object.__setattr__(encoder, "_grad_group_hook", None)
+
     def _on_group_ready(self, gi: int) -> None:
         ov = self._overlap
         if gi == -1 and ov["fired"] != 0:
