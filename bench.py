@@ -180,8 +180,8 @@ def workload_config(args, cpu_sample=None):
     cfg = {"workload": "hash-grid G4 (L16 F2 T2^19 base16 finest2489, 15.28M table params) + 2x64 GELU decoder "
                        "fitted to sample_ankle_dyn_mri.nii.gz (352x352x6x15, xyzt coords), Adam lr 5e-3",
            "batch_per_gpu": 1 << args.batch_log2, "global_batch": (1 << args.batch_log2) * args.gpus,
-           "parallelism": f"dp{args.gpus}" + (" (gradient all-reduce bucketed per 4 hash levels, overlapped with the "
-                                                 "scatter backward)" if args.gpus > 1 else ""), "l2": "inputs larger than L2: Adam streams 428 MB of p/g/m/v every step "
+           "parallelism": f"dp{args.gpus}" + (" (one NCCL all-reduce of the 61 MB flat gradient arena per step)"
+                                                 if args.gpus > 1 else ""), "l2": "inputs larger than L2: Adam streams 428 MB of p/g/m/v every step "
                                                   "(tables+grads+moments 244 MB > 126 MB L2)"}
     if cpu_sample:
         cfg["cpu_sample_coords_per_step"] = cpu_sample
@@ -208,7 +208,9 @@ def main():
     torch.manual_seed(1337)
     model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
     opt = model.configure_optimizers()
-    overlap = opt.enable_overlap(model.encoder, n_groups=4) if world > 1 else False
+    # bucketed/overlapped all-reduce is available but measured SLOWER at W=2 (1.608 vs 1.561 ms/step): the scatter
+    # backward and NCCL's copy kernels both saturate the L2, so the default stays one all-reduce after backward
+    overlap = opt.enable_overlap(model.encoder, n_groups=4) if (world > 1 and os.environ.get("MRI_DP_OVERLAP") == "1") else False
     vol = nifti.load(SAMPLE).get_fdata(np.float32)
     pix = torch.from_numpy(vol).flatten()
     pix = ((pix - pix.min()) / (pix.max() - pix.min())).to(dev)

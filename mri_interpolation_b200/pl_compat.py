@@ -257,9 +257,9 @@ class Trainer:
         if ckpt_path:
             model.load_state_dict(torch.load(ckpt_path, map_location=device, weights_only=False)["state_dict"])
         self.optimizer = self._first_optimizer(model.configure_optimizers())
-        if (self.accumulate_grad_batches is None and hasattr(self.optimizer, "enable_overlap")
-                and hasattr(getattr(model, "encoder", None), "tables")):
-            self.optimizer.enable_overlap(model.encoder)  # no-op unless torch.distributed runs with world_size > 1
+        if (os.environ.get("MRI_DP_OVERLAP") == "1" and self.accumulate_grad_batches is None
+                and hasattr(self.optimizer, "enable_overlap") and hasattr(getattr(model, "encoder", None), "tables")):
+            self.optimizer.enable_overlap(model.encoder)  # opt-in: bucketed all-reduce overlapped with the backward
         model.on_fit_start()
         model.on_train_start()
         t0 = time.time()
