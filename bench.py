@@ -40,18 +40,36 @@ SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (con
 HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
 
 
+WORKLOADS = {
+    # name: (description, default log2 batch per GPU)
+    "ankle_hash": ("hash-grid G4 (L16 F2 T2^19 base16 finest2489, 15.28M table params) + 2x64 GELU decoder fitted to "
+                   "sample_ankle_dyn_mri.nii.gz (352x352x6x15, xyzt coords), Adam lr 5e-3", 19),
+    "synthetic_hash": ("config 4: hash-grid G4 + 2x64 GELU decoder on a synthetic 256^3 x 32-frame volume (536.9M voxels, "
+                       "sum of separable sinusoids + noise, generated on device), Adam lr 5e-3", 19),
+    "siren_wide": ("config 5: SirenNet 3 -> 1024 x 8 -> 1 (w0 30) on a synthetic 512^3 volume, coords in [-1,1], "
+                   "tensor-core split-precision mode bf16x3 (fp32 parity), Adam lr 1e-4", 17),
+    "siren_ankle": ("config 1: SirenNet 4 -> 256 x 5 -> 1 (w0 30) on sample_ankle_dyn_mri.nii.gz, tensor-core "
+                    "split-precision mode bf16x3 (fp32 parity), Adam lr 1e-4", 18),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-log2", type=int, default=19)
+    ap.add_argument("--batch-log2", type=int, default=None, help="log2 coordinates per step per GPU (default per workload)")
+    ap.add_argument("--workload", default="ankle_hash", choices=list(WORKLOADS),
+                    help="ankle_hash = BASELINE configs[1] (default, the driver's bench line); the others are configs 1/4/5")
     ap.add_argument("--cpu-batch-log2", type=int, default=15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch_log2 is None:
+        args.batch_log2 = WORKLOADS[args.workload][1]
+    return args
 
 
 def peaks():
@@ -159,6 +177,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if args.workload != "ankle_hash":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the default "
+                          "workload (ankle_hash, BASELINE configs[1]) only"}))
+        return
     steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     value, dt, n = time_oracle(args.cpu_batch_log2, steps, warm)
     cores = torch.get_num_threads()
@@ -177,26 +199,80 @@ def run_reference(args):
 
 
 def workload_config(args, cpu_sample=None):
-    cfg = {"workload": "hash-grid G4 (L16 F2 T2^19 base16 finest2489, 15.28M table params) + 2x64 GELU decoder "
-                       "fitted to sample_ankle_dyn_mri.nii.gz (352x352x6x15, xyzt coords), Adam lr 5e-3",
+    cfg = {"workload": WORKLOADS[args.workload][0], "workload_name": args.workload,
            "batch_per_gpu": 1 << args.batch_log2, "global_batch": (1 << args.batch_log2) * args.gpus,
            "parallelism": f"dp{args.gpus}" + (" (one NCCL all-reduce of the 61 MB flat gradient arena per step)"
-                                                 if args.gpus > 1 else ""), "l2": "inputs larger than L2: Adam streams 428 MB of p/g/m/v every step "
-                                                  "(tables+grads+moments 244 MB > 126 MB L2)"}
+                                                 if args.gpus > 1 else ""), "l2": "inputs larger than L2: every step streams the whole p/g/m/v arena through Adam "
+                                                  "(hash: 489 MB/step) plus per-batch activations (SIREN: > 1 GB/layer)"}
     if cpu_sample:
         cfg["cpu_sample_coords_per_step"] = cpu_sample
     return cfg
 
 
 # -------------------------------------------------------------------------------------------------- B200 arm
+def synthetic_volume(shape, dev, seed=1337):
+    """Deterministic smooth + noise field on the device (config 4/5): sum of separable sinusoids + 1% hash noise."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.zeros(shape, device=dev, dtype=torch.float32)
+    for k in range(4):
+        term = torch.ones(shape, device=dev, dtype=torch.float32)
+        for d, s in enumerate(shape):
+            f = 1 + ((seed + 3 * k + d) % 5)
+            ph = 0.37 * (k + 1) * (d + 1)
+            view = [1] * len(shape)
+            view[d] = s
+            term = term * torch.sin(torch.linspace(0, 1, s, device=dev) * (6.2831853 * f) + ph).reshape(view)
+        out += term
+    out += 0.04 * torch.rand(shape, device=dev, generator=g)
+    out = (out - out.min()) / (out.max() - out.min())
+    return out.flatten()
+
+
+def build_workload(args, dev, rank):
+    from mri_interpolation_b200 import models, nifti
+    from mri_interpolation_b200 import functional as Fn
+    torch.manual_seed(1337)
+    name = args.workload
+    info = {}
+    if name in ("ankle_hash", "synthetic_hash"):
+        model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
+        info["train_flops_per_coord"] = None
+    elif name == "siren_wide":
+        model = models.SirenNet(dim_in=3, dim_hidden=1024, dim_out=1, n_layers=8, w0=30.0, w0_initial=30.0, lr=1e-4).to(dev)
+        info["fwd_flops_per_coord"], info["train_flops_per_coord"] = 14.688e6, 44.06e6
+    else:
+        model = models.SirenNet(dim_in=4, dim_hidden=256, dim_out=1, n_layers=5, w0=30.0, w0_initial=30.0, lr=1e-4).to(dev)
+        info["fwd_flops_per_coord"], info["train_flops_per_coord"] = 0.527e6, 1.58e6
+    norm_siren = name.startswith("siren")
+    if name in ("ankle_hash", "siren_ankle"):
+        vol = nifti.load(SAMPLE).get_fdata(np.float32)
+        shape = vol.shape
+        pix = torch.from_numpy(vol).flatten()
+        pix = ((pix - pix.min()) / (pix.max() - pix.min())).to(dev)
+    elif name == "synthetic_hash":
+        shape = (256, 256, 256, 32)
+        pix = synthetic_volume(shape, dev)
+    else:
+        shape = (512, 512, 512)
+        pix = synthetic_volume(shape, dev)
+    if norm_siren:
+        pix = pix * 2 - 1
+    sampler = Fn.VoxelSampler(pix, shape, norm_siren=norm_siren)
+    info["shape"] = shape
+    info["data"] = ("sample_ankle_dyn_mri.nii.gz (bundled reference sample volume)" if "ankle" in name
+                    else f"synthetic {'x'.join(map(str, shape))} volume generated on device") + ", random-init weights (seed 1337)"
+    return model, sampler, info
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
 
-    from mri_interpolation_b200 import _lib, distributed, models, nifti, sweep
-    from mri_interpolation_b200 import functional as Fn
+    from mri_interpolation_b200 import _lib, distributed, sweep
+    from mri_interpolation_b200.datamodules import PrefetchLoader
 
     rank, local_rank, world = distributed.init_from_env("nccl")
     if not torch.cuda.is_available():
@@ -205,17 +281,15 @@ def main():
     torch.cuda.set_device(dev)
     import torch.distributed as dist
 
-    torch.manual_seed(1337)
-    model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
+    model, sampler, info = build_workload(args, dev, rank)
+    is_hash = args.workload.endswith("hash")
     opt = model.configure_optimizers()
     # bucketed/overlapped all-reduce is available but measured SLOWER at W=2 (1.608 vs 1.561 ms/step): the scatter
     # backward and NCCL's copy kernels both saturate the L2, so the default stays one all-reduce after backward
-    overlap = opt.enable_overlap(model.encoder, n_groups=4) if (world > 1 and os.environ.get("MRI_DP_OVERLAP") == "1") else False
-    vol = nifti.load(SAMPLE).get_fdata(np.float32)
-    pix = torch.from_numpy(vol).flatten()
-    pix = ((pix - pix.min()) / (pix.max() - pix.min())).to(dev)
-    sampler = Fn.VoxelSampler(pix, vol.shape)
+    if is_hash and world > 1 and os.environ.get("MRI_DP_OVERLAP") == "1":
+        opt.enable_overlap(model.encoder, n_groups=4)
     n = 1 << args.batch_log2
+    dim = len(info["shape"])
     gen = torch.Generator(device=dev)
     gen.manual_seed(1337 + rank)
     total_steps = args.steps + args.warmup
@@ -255,15 +329,13 @@ def main():
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = float(t.item()) / args.steps
     value = n * world / (ms_step * 1e-3)
     final_loss = float(loss.detach())
 
     # ---- e2e: host batches through the public API (PrefetchLoader + LightningModule.training_step + FusedAdam)
     # every step: H2D copy of that step's batch from pinned host memory (overlapped with the previous step's
     # compute on a side stream) and a D2H read of that step's loss (async copy, consumed one step later).
-    from mri_interpolation_b200.datamodules import PrefetchLoader
     host_ring = []
     for r in range(4):
         xb, yb = sampler.batch(index[r])
@@ -303,16 +375,46 @@ def main():
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = n * world / float(e2e_dt.item())
 
+    # ---- inference: every rank sweeps its slab of the query volume (no communication), max over ranks
+    infer = None
+    if not args.no_infer:
+        if is_hash:
+            sweep_shape = SWEEP_SHAPE if args.workload == "ankle_hash" else (256, 256, 256, 4)
+        else:
+            sweep_shape = (352, 352, 6, 29) if args.workload == "siren_ankle" else (256, 256, 128)
+        total_vox = int(np.prod(sweep_shape))
+        ns = not is_hash
+        for _ in range(2):
+            sweep.dense_sweep(model, sweep_shape, norm_siren=ns, rank=rank, world_size=world)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 3
+        for _ in range(reps):
+            out = sweep.dense_sweep(model, sweep_shape, norm_siren=ns, rank=rank, world_size=world)
+        b.record()
+        barrier()
+        sw = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(sw, op=dist.ReduceOp.MAX)
+        sw_ms = float(sw.item())
+        t1 = time.perf_counter()
+        host = out.cpu()
+        d2h_s = time.perf_counter() - t1
+        infer = {"metric": "infer_voxels_per_s", "value": total_vox / (sw_ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+                 "workload": f"dense sweep of {sweep_shape} ({total_vox} voxels), contiguous slab per GPU, "
+                             + ("fused hash+decoder kernel" if is_hash else "coordinate synthesis + tensor-core SIREN"),
+                 "ms": sw_ms, "e2e_value_with_d2h": total_vox / (sw_ms * 1e-3 + d2h_s)}
+        del host, out
+
     # ---- isolated kernel timings for the roofline (rank 0, L2 flushed between launches)
-    roof, kern, infer = None, None, None
-    opt.disable_overlap(model.encoder)
+    roof, kern = None, None
+    if is_hash:
+        opt.disable_overlap(model.encoder)
     opt.data_parallel = False  # the isolated-kernel section below runs on rank 0 only: no collectives in it
     if rank == 0:
-        peak, peak_src = peaks()
+        hbm_peak, peak_src = peaks()
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        enc = model.encoder
-        x, y = sampler.batch(index[0])
-        go = torch.randn(n, 32, device=dev)
 
         def timed(fn, reps=10):
             times = []
@@ -324,52 +426,63 @@ def main():
                 a.record(); fn(); b.record()
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b))
-            return float(np.mean(times)), float(np.min(times))
+            return float(np.mean(times))
 
-        with torch.no_grad():
-            fwd_ms, fwd_min = timed(lambda: enc(x))
-        enc_out = enc(x)
-
-        def bwd():
-            torch.autograd.backward(enc_out, go, retain_graph=True)
-        bwd_ms, bwd_min = timed(bwd)
-        opt.arena.grad.zero_()
-        adam_ms, adam_min = timed(lambda: opt.step())
-        hash_bytes = HASH_BYTES_PER_COORD * n
-        adam_bytes = 32 * opt.arena.numel  # p,g,m,v read; p,m,v,g written (fused gradient clear)
-        kern = {
-            "hashgrid_fwd": {"ms": fwd_ms, "GBps_algorithmic": hash_bytes / fwd_ms / 1e6, "frac": hash_bytes / fwd_ms / 1e6 / peak},
-            "hashgrid_bwd": {"ms": bwd_ms, "GBps_algorithmic": hash_bytes / bwd_ms / 1e6, "frac": hash_bytes / bwd_ms / 1e6 / peak},
-            "adam_step": {"ms": adam_ms, "GBps_algorithmic": adam_bytes / adam_ms / 1e6, "frac": adam_bytes / adam_ms / 1e6 / peak},
-        }
-        top = "hashgrid_bwd" if bwd_ms >= fwd_ms else "hashgrid_fwd"
-        roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": peak, "unit": "GB/s",
-                "frac": kern[top]["frac"], "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": hash_bytes,
-                "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding); tables (61 MB) fit in "
-                        "the 126 MB L2, so DRAM traffic is far below the algorithmic bytes - see profiles/"}
-        # ---- inference: fused dense-grid sweep (config 3), voxels/s
-        if not args.no_infer:
-            total_vox = int(np.prod(SWEEP_SHAPE))
-            for _ in range(2):
-                sweep.dense_sweep(model, SWEEP_SHAPE)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            reps = 3
-            for _ in range(reps):
-                out = sweep.dense_sweep(model, SWEEP_SHAPE)
-            b.record(); torch.cuda.synchronize()
-            sw_ms = a.elapsed_time(b) / reps
-            t1 = time.perf_counter()
-            host = out.reshape(SWEEP_SHAPE).cpu()
-            d2h_s = time.perf_counter() - t1
-            infer = {"metric": "infer_voxels_per_s", "value": total_vox / (sw_ms * 1e-3), "unit": "voxels/s",
-                     "workload": f"fused hash+decoder sweep of {SWEEP_SHAPE} ({total_vox} voxels), 1 GPU slab",
-                     "ms": sw_ms, "e2e_value_with_d2h": total_vox / (sw_ms * 1e-3 + d2h_s)}
+        if is_hash:
+            enc = model.encoder
+            x, y = sampler.batch(index[0])
+            go = torch.randn(n, 32, device=dev)
+            with torch.no_grad():
+                fwd_ms = timed(lambda: enc(x))
+            enc_out = enc(x)
+            bwd_ms = timed(lambda: torch.autograd.backward(enc_out, go, retain_graph=True))
+            opt.arena.grad.zero_()
+            adam_ms = timed(lambda: opt.step())
+            hash_bytes = HASH_BYTES_PER_COORD * n
+            adam_bytes = 32 * opt.arena.numel  # p,g,m,v read; p,m,v,g written (fused gradient clear)
+            kern = {
+                "hashgrid_fwd": {"ms": fwd_ms, "GBps_algorithmic": hash_bytes / fwd_ms / 1e6, "frac": hash_bytes / fwd_ms / 1e6 / hbm_peak},
+                "hashgrid_bwd": {"ms": bwd_ms, "GBps_algorithmic": hash_bytes / bwd_ms / 1e6, "frac": hash_bytes / bwd_ms / 1e6 / hbm_peak},
+                "adam_step": {"ms": adam_ms, "GBps_algorithmic": adam_bytes / adam_ms / 1e6, "frac": adam_bytes / adam_ms / 1e6 / hbm_peak},
+            }
+            top = "hashgrid_bwd" if bwd_ms >= fwd_ms else "hashgrid_fwd"
+            roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kern[top]["frac"], "traffic": 320.7e6 if top == "hashgrid_bwd" else 235.2e6,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": hash_bytes,
+                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x 2^19 coords; traffic = ncu "
+                            "dram read+write per launch (profiles/r01_ncu_full_hash_adam.csv): the 61 MB of tables stay in "
+                            "the 126 MB L2, the kernel is bound by the L1/L2 sector rate (lts 76%, l1tex 74-88% of peak)"}
+        else:
+            from mri_interpolation_b200 import tc
+            from mri_interpolation_b200._lib import ACT_SINE
+            h = model.dim_hidden
+            a_f = torch.rand(n, h, device=dev) * 2 - 1
+            w_f = model.layers[1].weight.detach()
+            a_hi, a_lo = tc.split(a_f)
+            w_hi, w_lo = tc.split(w_f)
+            bias = model.layers[1].bias.detach()
+            ms_l = timed(lambda: tc.layer(a_hi, a_lo, w_hi, w_lo, bias, ACT_SINE, 30.0, passes=3, want_planes=True, want_aux=True), reps=5)
+            gw = torch.zeros(h, h, device=dev)
+            ms_w = timed(lambda: tc.wgrad(a_hi, a_lo, a_hi, a_lo, gw, None, passes=3), reps=5)
+            tf_peak = 1649.2
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.isfile(pk):
+                tf_peak = float(json.load(open(pk))["bf16_tflops"])
+            issued = 3 * 2.0 * n * h * h
+            kern = {"siren_tc_layer_fwd": {"ms": ms_l, "issued_bf16_TFLOPs": issued / ms_l / 1e9, "frac": issued / ms_l / 1e9 / tf_peak},
+                    "siren_tc_wgrad": {"ms": ms_w, "issued_bf16_TFLOPs": issued / ms_w / 1e9, "frac": issued / ms_w / 1e9 / tf_peak}}
+            roof = {"kernel": "siren_tc_layer_kernel (hidden layer forward, bf16x3 split precision, sine epilogue)",
+                    "bound": "tensor", "achieved": kern["siren_tc_layer_fwd"]["issued_bf16_TFLOPs"], "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": kern["siren_tc_layer_fwd"]["frac"], "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)",
+                    "algorithmic_flops_per_launch": 2.0 * n * h * h,
+                    "note": "issued = 3 tcgen05.mma passes x 2 n H^2 (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi); the fp32-equivalent "
+                            "(algorithmic) rate is one third of it"}
+            if info.get("train_flops_per_coord"):
+                kern["whole_step_algorithmic_TFLOPs"] = info["train_flops_per_coord"] * n / (ms_step * 1e-3) / 1e12
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and args.workload == "ankle_hash":
         v, dt, ncpu = time_oracle(args.cpu_batch_log2, 3, 1)
         cpu = {"value": v, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"3 steps of 2^{args.cpu_batch_log2} coords of the same training step (oracle port of the "
@@ -379,16 +492,16 @@ def main():
         line = {
             "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32",
-            "data": "sample_ankle_dyn_mri.nii.gz (bundled reference sample volume), random-init weights (seed 1337)",
-            "config": workload_config(args), "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": n * 20, "d2h_bytes_per_step": 4,
+            "vs_baseline": None, "dtype": "f32" if is_hash else "f32 via bf16x3 split on tcgen05 (fp32 accumulate)",
+            "data": info["data"], "config": workload_config(args), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": n * (dim + 1) * 4, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": launches, "final_loss": final_loss,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "infer": infer,
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
