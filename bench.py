@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 G4 = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, finest_resolution=2489)
 SAMPLE = os.path.join(ROOT, "data", "sample_ankle_dyn_mri.nii.gz")
 SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (config 3)
+PRIMING_STEPS = 15  # allocator priming before the W warm-up steps (reported in config)
 HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
 
 
@@ -90,9 +91,11 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if os.environ.get("MRI_BENCH_NO_CLOCKS") == "1":
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MRI_BENCH_CLOCK_MS", "50")], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -204,6 +207,7 @@ def workload_config(args, cpu_sample=None):
            "parallelism": f"dp{args.gpus}" + (" (one NCCL all-reduce of the 61 MB flat gradient arena per step)"
                                                  if args.gpus > 1 else ""), "l2": "inputs larger than L2: every step streams the whole p/g/m/v arena through Adam "
                                                   "(hash: 489 MB/step) plus per-batch activations (SIREN: > 1 GB/layer)"}
+    cfg["allocator_priming_steps_before_warmup"] = PRIMING_STEPS
     if cpu_sample:
         cfg["cpu_sample_coords_per_step"] = cpu_sample
     return cfg
@@ -310,6 +314,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    for i in range(PRIMING_STEPS):  # untimed: lets torch's caching allocator reach its steady state (no cudaMalloc later)
+        step(i)
     for i in range(args.warmup):
         step(i)
     barrier()
