@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -83,28 +82,26 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (subprocess writing to a temp file:
+    no Python reader thread competing with the launch loop for the GIL)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.path = index, None, None
 
     def start(self):
         if os.environ.get("MRI_BENCH_NO_CLOCKS") == "1":
             return
         try:
+            import tempfile
+            fd, self.path = tempfile.mkstemp(prefix="mri_clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MRI_BENCH_CLOCK_MS", "50")], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MRI_BENCH_CLOCK_MS", "50")],
+                                         stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
         except Exception:  # noqa: BLE001
             self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
         if self.proc is None:
@@ -114,21 +111,26 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        try:
+            lines = open(self.path).read().splitlines()
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            lines = []
+        sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
             except ValueError:
                 continue
             for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
