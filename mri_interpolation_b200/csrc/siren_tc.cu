@@ -34,6 +34,7 @@ struct LayerParams {
   int num_m_tiles, num_n_tiles;
   uint32_t stage_bytes, a_plane_bytes, b_plane_bytes;
   int act;
+  int b_mn_major;          // 0: B = W (m, k) K-major (forward); 1: B given as (k, m) row-major, i.e. MN-major (dgrad on W itself)
   float w0;
   const float* bias;       // (m) or null
   const float* mul;        // (n_rows, m) or null: elementwise factor applied to the result (dgrad: act')
@@ -120,6 +121,19 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // stride between 64-element MN groups
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride between 8-row K groups
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mnmajor(int m, int n) {
+  return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -185,9 +199,20 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             tma_load_2d(bptr, &map_a_lo, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
             bptr += p.a_plane_bytes;
           }
-          tma_load_2d(bptr, &map_b_hi, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
-          if (p.passes == 3)
-            tma_load_2d(bptr + p.b_plane_bytes, &map_b_lo, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+          if (!p.b_mn_major) {
+            tma_load_2d(bptr, &map_b_hi, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+            if (p.passes == 3)
+              tma_load_2d(bptr + p.b_plane_bytes, &map_b_lo, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+          } else {
+            // B stored (k, m) row-major: boxes of 64 output columns x 64 k-rows -> canonical MN-major SW128 groups
+            const int groups = p.block_n / 64;
+            for (int g = 0; g < groups; ++g)
+              tma_load_2d(bptr + g * (BLOCK_K * 128), &map_b_hi, &full_bar[stage], n_tile * p.block_n + g * 64, kb * BLOCK_K);
+            if (p.passes == 3)
+              for (int g = 0; g < groups; ++g)
+                tma_load_2d(bptr + p.b_plane_bytes + g * (BLOCK_K * 128), &map_b_lo, &full_bar[stage],
+                            n_tile * p.block_n + g * 64, kb * BLOCK_K);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -195,7 +220,7 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.block_n);
+    const uint32_t idesc = make_idesc_bf16(BLOCK_M, p.block_n) | (p.b_mn_major ? (1u << 16) : 0u);
     int stage = 0;
     uint32_t phase = 0;
     int acc_stage = 0;
@@ -215,12 +240,16 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
 #pragma unroll
           for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
             const uint32_t koff = ks * UMMA_K * 2;  // bytes along the swizzled 128-byte row
+            const uint32_t koff_mn = ks * UMMA_K * 128;  // MN-major B: 16 k-rows of 128 bytes
             const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
-            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+            const uint64_t db_hi = p.b_mn_major ? make_mnmajor_sw128_desc(b_hi + koff_mn, BLOCK_K * 128)
+                                                : make_kmajor_sw128_desc(b_hi + koff);
             if (p.passes == 3) {
+              const uint64_t db_lo = p.b_mn_major ? make_mnmajor_sw128_desc(b_lo + koff_mn, BLOCK_K * 128)
+                                                  : make_kmajor_sw128_desc(b_lo + koff);
               // small cross terms first, then the dominant hi*hi term
               tcgen05_mma_f16(d_tmem, make_kmajor_sw128_desc(a_lo + koff), db_hi, idesc, (kb | ks) != 0);
-              tcgen05_mma_f16(d_tmem, da_hi, make_kmajor_sw128_desc(b_lo + koff), idesc, 1);
+              tcgen05_mma_f16(d_tmem, da_hi, db_lo, idesc, 1);
               tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
             } else {
               tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
@@ -341,18 +370,6 @@ struct WgradParams {
 
 constexpr int WG_BLOCK_K = 64;  // batch rows per stage
 
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;  // stride between 64-element MN groups
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride between 8-row K groups
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
-  return d;
-}
-__host__ __device__ constexpr uint32_t make_idesc_bf16_mnmajor(int m, int n) {
-  return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16);  // a_major = b_major = MN
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 siren_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_constant__ CUtensorMap map_g_lo,
@@ -577,9 +594,9 @@ extern "C" int mri_siren_tc_split(const float* src, int64_t count, void* hi, voi
   return MRI_OK;
 }
 
-extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
-                                  int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
-                                  void* out_lo, float* out_f32, float* aux_f32, void* stream) {
+static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
+                               void* out_lo, float* out_f32, float* aux_f32, int b_mn_major, void* stream) {
   if (!a_hi || !w_hi) return fail(MRI_ERR_INVALID, "siren_tc_layer: null operand");
   if (passes != 1 && passes != 3) return fail(MRI_ERR_INVALID, "siren_tc_layer: passes must be 1 (bf16) or 3 (split fp32)");
   if (passes == 3 && (!a_lo || !w_lo)) return fail(MRI_ERR_INVALID, "siren_tc_layer: lo planes required for passes=3");
@@ -590,7 +607,7 @@ extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void
   if (!out_hi && !out_f32) return fail(MRI_ERR_INVALID, "siren_tc_layer: no output requested");
 
   tc::LayerParams p{};
-  p.n_rows = n; p.k = k; p.m = m; p.passes = passes; p.act = act; p.w0 = w0;
+  p.n_rows = n; p.k = k; p.m = m; p.passes = passes; p.act = act; p.w0 = w0; p.b_mn_major = b_mn_major;
   p.block_n = tc::pick_block_n(m);
   p.num_m_tiles = static_cast<int>((n + tc::BLOCK_M - 1) / tc::BLOCK_M);
   p.num_n_tiles = m / p.block_n;
@@ -609,8 +626,13 @@ extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void
   int st;
   if ((st = tc::make_map(&ma_hi, a_hi, n, k, tc::BLOCK_M)) != MRI_OK) return st;
   if ((st = tc::make_map(&ma_lo, passes == 3 ? a_lo : a_hi, n, k, tc::BLOCK_M)) != MRI_OK) return st;
-  if ((st = tc::make_map(&mb_hi, w_hi, m, k, p.block_n)) != MRI_OK) return st;
-  if ((st = tc::make_map(&mb_lo, passes == 3 ? w_lo : w_hi, m, k, p.block_n)) != MRI_OK) return st;
+  if (!b_mn_major) {
+    if ((st = tc::make_map(&mb_hi, w_hi, m, k, p.block_n)) != MRI_OK) return st;
+    if ((st = tc::make_map(&mb_lo, passes == 3 ? w_lo : w_hi, m, k, p.block_n)) != MRI_OK) return st;
+  } else {  // operand stored (k, m) row-major: boxes of 64 columns x 64 rows
+    if ((st = tc::make_map(&mb_hi, w_hi, k, m, tc::BLOCK_K)) != MRI_OK) return st;
+    if ((st = tc::make_map(&mb_lo, passes == 3 ? w_lo : w_hi, k, m, tc::BLOCK_K)) != MRI_OK) return st;
+  }
 
   const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
   MRI_CUDA_OK(cudaFuncSetAttribute(tc::siren_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -685,4 +707,19 @@ extern "C" int mri_siren_tc_mul_split(const float* a, const float* b, int64_t co
       a, b, count, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo));
   MRI_LAUNCH_OK("mul_split_kernel");
   return MRI_OK;
+}
+
+extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                  int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
+                                  void* out_lo, float* out_f32, float* aux_f32, void* stream) {
+  return siren_tc_layer_impl(a_hi, a_lo, w_hi, w_lo, bias, n, k, m, act, w0, passes, mul, out_hi, out_lo, out_f32, aux_f32, 0,
+                             stream);
+}
+
+extern "C" int mri_siren_tc_dgrad(const void* g_hi, const void* g_lo, const void* w_hi, const void* w_lo, int64_t n, int k,
+                                  int m, int passes, const float* mul, void* out_hi, void* out_lo, float* out_f32,
+                                  void* stream) {
+  // dX (n, k) = G (n, m) . W (m, k): W is consumed as stored (rows = the GEMM's K), i.e. as an MN-major B operand
+  return siren_tc_layer_impl(g_hi, g_lo, w_hi, w_lo, nullptr, n, /*gemm K=*/m, /*gemm N=*/k, MRI_ACT_IDENTITY, 1.0f, passes, mul,
+                             out_hi, out_lo, out_f32, nullptr, 1, stream);
 }

@@ -64,7 +64,7 @@ class SirenTcFn(torch.autograd.Function):
         wplanes = [None]
         last_f32 = None
         for i in range(1, n_hidden):
-            w_hi, w_lo = tc.split(ws[i], need_lo=(passes == 3))
+            w_hi, w_lo = tc.split(ws[i], need_lo=(passes == 3))  # weights change every optimiser step: re-split
             wplanes.append((w_hi, w_lo))
             is_last_hidden = i == n_hidden - 1
             oh, ol, of, aux = tc.layer(acts[-1][0], acts[-1][1], w_hi, w_lo, bs[i], ACT_SINE, w0s[i], passes=passes,
@@ -80,7 +80,7 @@ class SirenTcFn(torch.autograd.Function):
         _lib.call("mri_dense_forward", last_f32.data_ptr(), last_f32.stride(0), ws[-1].data_ptr(), bs[-1].data_ptr(), n,
                   h_dim, m_out, ACT_IDENTITY, 1.0, y.data_ptr(), None, _lib.stream())
         if train:
-            ctx.saved = (x2, pre0, acts, auxs, last_f32)
+            ctx.saved = (x2, pre0, acts, auxs, last_f32, wplanes)
             ctx.params = params
             ctx.w0s, ctx.passes = w0s, passes
         ctx.train = train
@@ -90,7 +90,7 @@ class SirenTcFn(torch.autograd.Function):
     def backward(ctx, grad_y):
         if not ctx.train:
             return (None,) * (3 + len(ctx.params))
-        x2, pre0, acts, auxs, last_f32 = ctx.saved
+        x2, pre0, acts, auxs, last_f32, wplanes = ctx.saved
         params, w0s, passes = ctx.params, ctx.w0s, ctx.passes
         ws, bs = params[0::2], params[1::2]
         n_hidden = len(w0s)
@@ -118,13 +118,11 @@ class SirenTcFn(torch.autograd.Function):
         for i in range(n_hidden - 1, 0, -1):
             x_hi, x_lo = acts[i - 1]
             tc.wgrad(g_hi, g_lo, x_hi, x_lo, gw[i], gb[i], passes=passes)
-            wt_hi, wt_lo = tc.split(ws[i].t().contiguous(), need_lo=(passes == 3))
+            w_hi, w_lo = wplanes[i]  # the forward's planes, read as an MN-major operand: no transpose
             if i > 1:
-                g_hi, g_lo, _, _ = tc.layer(g_hi, g_lo, wt_hi, wt_lo, None, ACT_IDENTITY, 1.0, passes=passes, mul=auxs[i - 1],
-                                            want_planes=True)
+                g_hi, g_lo, _ = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[i - 1], want_planes=True)
             else:
-                _, _, dh0, _ = tc.layer(g_hi, g_lo, wt_hi, wt_lo, None, ACT_IDENTITY, 1.0, passes=passes, want_planes=False,
-                                        want_f32=True)
+                _, _, dh0 = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, want_planes=False, want_f32=True)
         # layer 0 (CUDA cores): dpre0 = dh0 * w0 cos(w0 pre0); dW0, db0
         scratch = torch.empty_like(dh0)
         _lib.call("mri_dense_backward", x2.data_ptr(), x2.stride(0), ws[0].data_ptr(), pre0.data_ptr(), dh0.data_ptr(), n,

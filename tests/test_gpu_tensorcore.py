@@ -131,3 +131,21 @@ def test_sirennet_tensor_core_path_matches_oracle(kw, n):
     net.precision = "bf16"
     with torch.no_grad():
         assert rel_err(net(x.to(DEV)), pred_ref.detach()) < 5e-2  # bf16 mode: stated tolerance 5e-2
+
+
+@pytest.mark.parametrize("n,k,m", [(3000, 256, 256), (1000, 128, 512), (5000, 1024, 1024), (700, 512, 64)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_tc_dgrad_on_untransposed_weights(n, k, m, passes):
+    from mri_interpolation_b200 import tc
+    gen = torch.Generator(device=DEV).manual_seed(n + k + m)
+    g = torch.randn(n, m, device=DEV, generator=gen)
+    w = torch.randn(m, k, device=DEV, generator=gen) / m ** 0.5
+    mul = torch.randn(n, k, device=DEV, generator=gen)
+    g_hi, g_lo = tc.split(g)
+    w_hi, w_lo = tc.split(w)
+    oh, ol, of = tc.dgrad(g_hi, g_lo if passes == 3 else None, w_hi, w_lo if passes == 3 else None, passes=passes, mul=mul,
+                          want_f32=True)
+    ref = (g.double() @ w.double()) * mul.double()
+    assert rel_err(of, ref) < (3e-5 if passes == 3 else 8e-3)
+    if passes == 3:
+        assert rel_err(oh.float() + ol.float(), ref) < 5e-5
