@@ -327,8 +327,16 @@ def main():
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    inflight = []
     for i in range(args.warmup, total_steps):
         loss = step(i)
+        # bound the host's run-ahead to two steps (a saturated launch queue starves NCCL's progress thread and made
+        # multi-GPU SIREN steps ~25% slower); the GPU stays fed: the event waited on is two steps old
+        ev = torch.cuda.Event()
+        ev.record()
+        inflight.append(ev)
+        if len(inflight) > 2:
+            inflight.pop(0).synchronize()
     ev1.record()
     barrier()
     launches = _lib.launch_count - launches0
