@@ -33,15 +33,21 @@ __device__ __forceinline__ void act_and_grad(float pre, float& a, float& g) {
 }
 
 // hidden pre-activations of one coordinate: h[j] = b1[j] + sum_k enc[k] W1[j][k]  (W1t = W1 transposed in smem)
+// the whole encoding row of a coordinate: K0/4 independent 16-byte loads issued back-to-back (one latency, not K0/4)
+template <int K0>
+__device__ __forceinline__ void load_row(const float* __restrict__ enc_row, float4 (&e)[K0 / 4]) {
+#pragma unroll
+  for (int q = 0; q < K0 / 4; ++q) e[q] = __ldg(reinterpret_cast<const float4*>(enc_row) + q);
+}
+
 template <int K0, int H>
-__device__ __forceinline__ void hidden_pre(const float* __restrict__ enc_row, const float* __restrict__ w1t,
+__device__ __forceinline__ void hidden_pre(const float4 (&row)[K0 / 4], const float* __restrict__ w1t,
                                            const float* __restrict__ b1s, float (&h)[H]) {
 #pragma unroll
   for (int j = 0; j < H; ++j) h[j] = b1s[j];
-#pragma unroll 1
+#pragma unroll
   for (int k4 = 0; k4 < K0 / 4; ++k4) {
-    const float4 e4 = __ldg(reinterpret_cast<const float4*>(enc_row) + k4);
-    const float e[4] = {e4.x, e4.y, e4.z, e4.w};
+    const float e[4] = {row[k4].x, row[k4].y, row[k4].z, row[k4].w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const float4* row = reinterpret_cast<const float4*>(w1t + (4 * k4 + u) * H);
@@ -77,8 +83,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) decoder2_fwd_kernel(const floa
   __syncthreads();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * DEC_THREADS;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * DEC_THREADS + threadIdx.x; i < n; i += stride) {
+    float4 row[K0 / 4];
+    load_row<K0>(enc + i * K0, row);
     float h[H];
-    hidden_pre<K0, H>(enc + i * K0, w1t, b1s, h);
+    hidden_pre<K0, H>(row, w1t, b1s, h);
     float pre2 = b2v;
 #pragma unroll
     for (int j = 0; j < H; ++j) pre2 = fmaf(activate<ACT1>(h[j], 1.0f), w2s[j], pre2);
@@ -133,8 +141,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const floa
     {
       float h[H];
       float dp2 = 0.0f;
+      float4 row[K0 / 4];
+#pragma unroll
+      for (int q = 0; q < K0 / 4; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
-        hidden_pre<K0, H>(enc + i * K0, w1t, b1s, h);
+        load_row<K0>(enc + i * K0, row);
+        hidden_pre<K0, H>(row, w1t, b1s, h);
         dp2 = __ldg(gy + i) * activate_grad_rt(act2, __ldg(pre2 + i), 1.0f);
         acc_b2 += dp2;
       } else {
@@ -156,9 +168,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const floa
         ad_row[q] = make_float4(a[0], a[1], a[2], a[3]);
       }
       // dEnc[k] = sum_j dPre1[j] W1[j][k], four k at a time; park enc (transposed) for the dW1 phase
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < K0 / 4; ++q) {
-        float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 e4 = row[q];
         if (live) {
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -168,7 +180,6 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const floa
             acc.z = fmaf(h[j], w.z, acc.z); acc.w = fmaf(h[j], w.w, acc.w);
           }
           reinterpret_cast<float4*>(denc + i * K0)[q] = acc;
-          e4 = __ldg(reinterpret_cast<const float4*>(enc + i * K0) + q);
         }
         enc_t[(4 * q + 0) * (DEC_THREADS + 1) + threadIdx.x] = e4.x;
         enc_t[(4 * q + 1) * (DEC_THREADS + 1) + threadIdx.x] = e4.y;
