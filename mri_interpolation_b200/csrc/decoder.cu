@@ -8,6 +8,9 @@
 //                         dW1 (H x K0, a reduction over the batch) is formed per 128-coordinate chunk from
 //                         shared-memory copies of dPre1 and enc, accumulated in registers across the
 //                         persistent block's chunks and flushed once per block with red.global.add.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mri {
@@ -225,6 +228,140 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const floa
   if ((threadIdx.x & 31) == 0) red_add_f32(gb2, acc_b2);
 }
 
+// ================================ tensor-core (mma.sync) variant ====================================
+// The hidden layer enc(K0) -> H is a (32 coords x K0) x (K0 x H) product per warp: tiny for tcgen05/TMEM tiles, but
+// a good fit for warp-level mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) with the same split-precision trick
+// as the SIREN path (x = hi + lo; A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), which keeps fp32 parity.  Fragments come
+// straight from global memory (A: float2 loads in the fragment's own (row g, cols 2t) pattern) and from a padded
+// bf16 copy of W1 in shared memory (B); bias, GELU, the H -> 1 output layer and its quad reduction happen on the
+// accumulator fragments in registers.  ~3x fewer issued instructions than the CUDA-core kernel above.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
+  const __nv_bfloat162 h = __halves2bfloat162(hx, hy);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __bfloat162float(hx), y - __bfloat162float(hy));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int MMA_PAD = 8;  // bf16 elements of row padding: conflict-free 32-bit fragment loads
+
+// W (rows x cols, fp32, row-major in global) -> two padded bf16 planes in shared memory
+template <int ROWS, int COLS>
+__device__ __forceinline__ void stage_planes(const float* __restrict__ w, __nv_bfloat16* hi, __nv_bfloat16* lo, bool transpose) {
+  for (int e = threadIdx.x; e < ROWS * COLS; e += DEC_THREADS) {
+    const int r = e / COLS, c = e - r * COLS;
+    const float v = __ldg(w + e);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const int dst = transpose ? (c * (ROWS + MMA_PAD) + r) : (r * (COLS + MMA_PAD) + c);
+    hi[dst] = h;
+    lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// A fragments (hi/lo) of one 16-coordinate m-tile: rows (g, g+8) of `enc`, all K0 columns
+template <int K0>
+__device__ __forceinline__ void load_a_frags(const float* __restrict__ enc, int64_t row0, int64_t n, int g, int t,
+                                             uint32_t (&a_hi)[K0 / 16][4], uint32_t (&a_lo)[K0 / 16][4]) {
+  const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
+#pragma unroll
+  for (int kt = 0; kt < K0 / 16; ++kt) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int col = 16 * kt + 8 * half + 2 * t;
+      float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+      if (r_lo < n) v0 = __ldg(reinterpret_cast<const float2*>(enc + r_lo * K0 + col));
+      if (r_hi < n) v1 = __ldg(reinterpret_cast<const float2*>(enc + r_hi * K0 + col));
+      split_pair(v0.x, v0.y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
+      split_pair(v1.x, v1.y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+    }
+  }
+}
+
+// acc[nt] (16 x 8 tiles over the H hidden units) = bias + A . W1^T with the 3-pass split product
+template <int K0, int H>
+__device__ __forceinline__ void hidden_mma(const uint32_t (&a_hi)[K0 / 16][4], const uint32_t (&a_lo)[K0 / 16][4],
+                                           const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo,
+                                           const float* __restrict__ b1s, int g, int t, float (&acc)[H / 8][4]) {
+  constexpr int WS = K0 + MMA_PAD;
+#pragma unroll
+  for (int nt = 0; nt < H / 8; ++nt) {
+    const float bl = b1s[8 * nt + 2 * t], bh = b1s[8 * nt + 2 * t + 1];
+    acc[nt][0] = bl; acc[nt][1] = bh; acc[nt][2] = bl; acc[nt][3] = bh;
+#pragma unroll
+    for (int kt = 0; kt < K0 / 16; ++kt) {
+      const int off = (8 * nt + g) * WS + 16 * kt + 2 * t;
+      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(w_hi + off), bh1 = *reinterpret_cast<const uint32_t*>(w_hi + off + 8);
+      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(w_lo + off), bl1 = *reinterpret_cast<const uint32_t*>(w_lo + off + 8);
+      mma_bf16_16816(acc[nt], a_lo[kt], bh0, bh1);
+      mma_bf16_16816(acc[nt], a_hi[kt], bl0, bl1);
+      mma_bf16_16816(acc[nt], a_hi[kt], bh0, bh1);
+    }
+  }
+}
+
+template <int K0, int H, int ACT1>
+__global__ void __launch_bounds__(DEC_THREADS, 3) decoder2_mma_fwd_kernel(const float* __restrict__ enc, int64_t n,
+                                                                           const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                           const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                           int act2, float* __restrict__ y, float* __restrict__ pre2_out) {
+  constexpr int WS = K0 + MMA_PAD;
+  __shared__ __align__(16) __nv_bfloat16 w_hi[H * WS];
+  __shared__ __align__(16) __nv_bfloat16 w_lo[H * WS];
+  __shared__ float b1s[H];
+  __shared__ float w2s[H];
+  stage_planes<H, K0>(w1, w_hi, w_lo, false);
+  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+    b1s[e] = __ldg(b1 + e);
+    w2s[e] = __ldg(w2 + e);
+  }
+  const float b2v = __ldg(b2);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t tiles = (n + 15) / 16;  // 16-coordinate m-tiles, one per warp iteration
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (DEC_THREADS / 32) + warp; tile < tiles;
+       tile += static_cast<int64_t>(gridDim.x) * (DEC_THREADS / 32)) {
+    const int64_t row0 = tile * 16;
+    uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
+    load_a_frags<K0>(enc, row0, n, g, t, a_hi, a_lo);
+    float acc[H / 8][4];
+    hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
+    // output layer on the fragments: this thread owns rows (g, g+8) x columns {8nt+2t, 8nt+2t+1}
+    float s_lo = 0.0f, s_hi = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < H / 8; ++nt) {
+      const float wl = w2s[8 * nt + 2 * t], wh = w2s[8 * nt + 2 * t + 1];
+      s_lo = fmaf(activate<ACT1>(acc[nt][0], 1.0f), wl, s_lo);
+      s_lo = fmaf(activate<ACT1>(acc[nt][1], 1.0f), wh, s_lo);
+      s_hi = fmaf(activate<ACT1>(acc[nt][2], 1.0f), wl, s_hi);
+      s_hi = fmaf(activate<ACT1>(acc[nt][3], 1.0f), wh, s_hi);
+    }
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+    if (t == 0) {
+      const int64_t r0 = row0 + g, r1 = row0 + g + 8;
+      if (r0 < n) { const float p = s_lo + b2v; y[r0] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[r0] = p; }
+      if (r1 < n) { const float p = s_hi + b2v; y[r1] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[r1] = p; }
+    }
+  }
+}
+
+template <int K0, int H, int ACT1>
+int launch_mma_fwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* b2, int act2,
+                   float* y, float* pre2, cudaStream_t s) {
+  int64_t blocks = ((n + 15) / 16 + 3) / 4;
+  const int64_t cap = 6LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  decoder2_mma_fwd_kernel<K0, H, ACT1><<<static_cast<int>(blocks), DEC_THREADS, 0, s>>>(enc, n, w1, b1, w2, b2, act2, y, pre2);
+  MRI_LAUNCH_OK("decoder2_mma_fwd_kernel");
+  return MRI_OK;
+}
+
 template <int K0, int H>
 size_t bwd_smem_bytes() {
   return sizeof(float) * (2 * K0 * H + 2 * H + 2 * DEC_THREADS * (H + DP_PAD) + K0 * (DEC_THREADS + 1));
@@ -287,6 +424,12 @@ extern "C" int mri_decoder2_forward(const float* enc, int64_t n, int k0, int h, 
     return fail(MRI_ERR_UNSUPPORTED, "decoder2_forward: no fused kernel for K0=%d H=%d act=%d", k0, h, act1);
   if (reinterpret_cast<uintptr_t>(enc) & 15) return fail(MRI_ERR_INVALID, "decoder2_forward: enc must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static const bool use_cuda_cores = getenv("MRI_DECODER_CUDA_CORES") != nullptr;  // debugging/profiling switch
+  if (!use_cuda_cores) {
+#define CALL(K0V, HV, ACTV) launch_mma_fwd<K0V, HV, ACTV>(enc, n, w1, b1, w2, b2, act2, y, pre2, s)
+    MRI_DEC_ALL(CALL)
+#undef CALL
+  }
 #define CALL(K0V, HV, ACTV) launch_fwd<K0V, HV, ACTV>(enc, n, w1, b1, w2, b2, act2, y, pre2, s)
   MRI_DEC_ALL(CALL)
 #undef CALL
