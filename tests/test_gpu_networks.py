@@ -220,7 +220,7 @@ def test_fused_decoder2_vs_torch(k0, h, act, n):
     ps = [p.detach().to(DEV).requires_grad_() for p in (l1.weight, l1.bias, l2.weight, l2.bias)]
     assert Fn.decoder2_supported(k0, h, code)
     y = Fn.Decoder2Fn.apply(encd, *ps, code, code)
-    assert rel_err(y, y_ref) < 1e-5
+    assert rel_err(y, y_ref) < 5e-5  # hidden layer on tensor cores, bf16x3 split precision (north_star bound: 1e-3)
     y.backward(gy.to(DEV))
     assert rel_err(encd.grad, enc.grad) < 1e-4
     for p, r in zip(ps, (l1.weight, l1.bias, l2.weight, l2.bias)):
