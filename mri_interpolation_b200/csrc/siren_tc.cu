@@ -12,8 +12,9 @@
 //              smem stages, completion on "full" mbarriers
 //   warp 1     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16) against
 //              smem descriptors, tcgen05.commit frees the stage ("empty") and publishes the accumulator
-//   warps 2-5  epilogue: tcgen05.ld the 128 x block_n fp32 accumulator out of TMEM (double-buffered: 2 x
-//              block_n columns), + bias, sin(w0 .) / w0 cos(w0 .) or * mul, stores bf16 hi/lo planes + f32
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, half of the columns each): tcgen05.ld the 128 x block_n
+//              fp32 accumulator out of TMEM (double-buffered: 2 x block_n columns), + bias, sin(w0 .) / w0 cos(w0 .)
+//              or * mul, stores bf16 hi/lo planes + f32
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -25,7 +26,8 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;          // wgrad kernel: producer, MMA, 4 epilogue warps
+constexpr int LAYER_THREADS = 320;        // layer kernel: producer, MMA, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct LayerParams {
@@ -140,7 +142,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // ---- the GEMM + fused epilogue ------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(LAYER_THREADS, 1)
 siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       const LayerParams p) {
@@ -165,7 +167,7 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -264,8 +266,10 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       if (++acc_stage == 2) { acc_stage = 0; acc_phase ^= 1; }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    // ================= epilogue (warps 2..9) =================
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int col_half = (warp - 2) >> 2;  // two warps per quarter: each takes half of the tile's columns
+    const int c_begin = col_half * (p.block_n / 2), c_end = c_begin + p.block_n / 2;
     int acc_stage = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -274,7 +278,7 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       tcgen05_fence_after();
       const int64_t row = static_cast<int64_t>(m_tile) * BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < p.n_rows;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc_stage * p.block_n + c0);
@@ -638,7 +642,7 @@ static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w
   MRI_CUDA_OK(cudaFuncSetAttribute(tc::siren_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc::siren_tc_layer_kernel<<<grid, tc::NUM_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  tc::siren_tc_layer_kernel<<<grid, tc::LAYER_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   MRI_LAUNCH_OK("siren_tc_layer_kernel");
   return MRI_OK;
 }

@@ -9,6 +9,6 @@ $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'hashgrid_fwd|hashgrid_bwd|adam_kernel' -s 6 -c 6 -f -o gpurun_out/prof_step $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit $?" | tee -a gpurun_out/status.txt
 $CMD > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'hashmlp_sweep|sgemm|dpre|gather_voxels|mse_kernel' -s 12 -c 9 -f -o gpurun_out/prof_rest $CMD > gpurun_out/ncu_full2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'hashmlp_sweep|decoder2|gather_voxels|mse_kernel' -s 16 -c 9 -f -o gpurun_out/prof_rest $CMD > gpurun_out/ncu_full2.log 2>&1
 echo "full capture 2 exit $?" | tee -a gpurun_out/status.txt
 ls -la gpurun_out

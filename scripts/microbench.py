@@ -157,3 +157,24 @@ prev.update(res)
 json.dump(prev, open(out, "w"), indent=1)
 for k, v in res.items():
     print(k, json.dumps(v))
+
+if "levels" in which:
+    # per-level cost of the scatter backward and the gather forward (G4, 2^19 random coords)
+    from mri_interpolation_b200 import _lib
+    torch.manual_seed(1337)
+    model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
+    enc = model.encoder
+    n = 1 << 19
+    x = torch.rand(n, 4, device=dev)
+    go = torch.randn(n, 32, device=dev)
+    tables = enc.tables()
+    grads = [torch.zeros_like(t) for t in tables]
+    enc._bwd_layout.refresh(grads, enc._resolutions, enc._rows)
+    per = {}
+    for lv in range(16):
+        ms, _ = timed(lambda: _lib.call("mri_hashgrid_backward_levels", x.data_ptr(), n, 4, go.data_ptr(), enc._bwd_layout.base,
+                                        enc._bwd_layout.levels, 16, 2, lv, 1, _lib.stream()), reps=5)
+        per[f"bwd_level_{lv}_rows_{enc._rows[lv]}"] = round(ms * 1e3, 1)
+    res["hashgrid_bwd_per_level_us"] = per
+    json.dump({**prev, **res}, open(out, "w"), indent=1)
+    print(json.dumps(per, indent=0))
