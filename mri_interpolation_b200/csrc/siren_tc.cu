@@ -141,6 +141,62 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+
+// ---- coalesced epilogue I/O ---------------------------------------------------------------------
+// After tcgen05.ld a lane owns one ROW of the tile (32 consecutive columns).  Storing that directly makes every
+// STG.128 touch 32 different 128-byte lines (32 L1 wavefronts per instruction), which - not the sine ALU work -
+// bounded the epilogue.  Each epilogue warp therefore transposes through a private 32 x 33-word shared-memory
+// patch so that one instruction writes 4 full rows of 128 contiguous bytes (f32) or 8 rows of 64 bytes (bf16).
+constexpr int EPI_PATCH_WORDS = 32 * 33;
+
+__device__ __forceinline__ void store_tile_f32(const float (&v)[32], float* patch, float* __restrict__ gbase, int64_t ld,
+                                               int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];
+  __syncwarp();
+  const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sub_row;
+    const float* src = patch + r * 33 + c4;
+    const float4 o = make_float4(src[0], src[1], src[2], src[3]);
+    if (r < rows_valid) *reinterpret_cast<float4*>(gbase + static_cast<int64_t>(r) * ld + c4) = o;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void load_tile_f32(float (&v)[32], float* patch, const float* __restrict__ gbase, int64_t ld,
+                                              int rows_valid, int lane) {
+  const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + sub_row;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows_valid) o = __ldg(reinterpret_cast<const float4*>(gbase + static_cast<int64_t>(r) * ld + c4));
+    float* dst = patch + r * 33 + c4;
+    dst[0] = o.x; dst[1] = o.y; dst[2] = o.z; dst[3] = o.w;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = patch[lane * 33 + j];
+  __syncwarp();
+}
+// 32 bf16 per row = 16 packed words
+__device__ __forceinline__ void store_tile_bf16(const uint32_t (&w)[16], uint32_t* patch, __nv_bfloat16* __restrict__ gbase,
+                                                int64_t ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) patch[lane * 17 + j] = w[j];
+  __syncwarp();
+  const int sub_row = lane >> 2, w4 = (lane & 3) * 4;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + sub_row;
+    const uint32_t* src = patch + r * 17 + w4;
+    const uint4 o = make_uint4(src[0], src[1], src[2], src[3]);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<int64_t>(r) * ld + 2 * w4) = o;
+  }
+  __syncwarp();
+}
+
 // ---- the GEMM + fused epilogue ------------------------------------------------------------------
 __global__ void __launch_bounds__(LAYER_THREADS, 1)
 siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -159,6 +215,8 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
   const int num_kb = p.k / BLOCK_K;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const uint32_t tmem_cols = 2u * static_cast<uint32_t>(p.block_n);  // power of two >= 128 (block_n in {64,128,256})
+  // per-epilogue-warp transposition patches live behind the operand ring
+  float* epi_patch = reinterpret_cast<float*>(smem + static_cast<size_t>(p.stages) * p.stage_bytes) + (warp >= 2 ? (warp - 2) : 0) * EPI_PATCH_WORDS;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -276,17 +334,18 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       mbar_wait(&tmem_full_bar[acc_stage], acc_phase);
       tcgen05_fence_after();
-      const int64_t row = static_cast<int64_t>(m_tile) * BLOCK_M + quarter * 32 + lane;
-      const bool row_ok = row < p.n_rows;
+      const int64_t row_base = static_cast<int64_t>(m_tile) * BLOCK_M + quarter * 32;  // first row of this warp's patch
+      const int64_t rows_left = p.n_rows - row_base;
+      const int rows_valid = rows_left < 0 ? 0 : (rows_left > 32 ? 32 : static_cast<int>(rows_left));
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                                static_cast<uint32_t>(acc_stage * p.block_n + c0);
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (rows_valid > 0) {  // warp-uniform
           const int col0 = n_tile * p.block_n + c0;
-          const int64_t off = row * p.m + col0;
+          const int64_t off = row_base * p.m + col0;  // element offset of the patch's top-left corner
           float out[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -302,24 +361,15 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
               aux[j] = p.w0 * __cosf(r);
               out[j] = __sinf(r);
             }
-            if (p.aux_f32) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                reinterpret_cast<float4*>(p.aux_f32 + off)[q] = make_float4(aux[4 * q], aux[4 * q + 1], aux[4 * q + 2], aux[4 * q + 3]);
-            }
+            if (p.aux_f32) store_tile_f32(aux, epi_patch, p.aux_f32 + off, p.m, rows_valid, lane);
           }
           if (p.mul) {
+            float f[32];
+            load_tile_f32(f, epi_patch, p.mul + off, p.m, rows_valid, lane);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 f = __ldg(reinterpret_cast<const float4*>(p.mul + off) + q);
-              out[4 * q] *= f.x; out[4 * q + 1] *= f.y; out[4 * q + 2] *= f.z; out[4 * q + 3] *= f.w;
-            }
+            for (int j = 0; j < 32; ++j) out[j] *= f[j];
           }
-          if (p.out_f32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              reinterpret_cast<float4*>(p.out_f32 + off)[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-          }
+          if (p.out_f32) store_tile_f32(out, epi_patch, p.out_f32 + off, p.m, rows_valid, lane);
           if (p.out_hi) {
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -329,14 +379,8 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
               hi[j] = pack_bf16x2(a, b);
               lo[j] = pack_bf16x2(a - __bfloat162float(ah), b - __bfloat162float(bh));
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              reinterpret_cast<uint4*>(p.out_hi + off)[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            if (p.out_lo) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                reinterpret_cast<uint4*>(p.out_lo + off)[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-            }
+            store_tile_bf16(hi, reinterpret_cast<uint32_t*>(epi_patch), p.out_hi + off, p.m, rows_valid, lane);
+            if (p.out_lo) store_tile_bf16(lo, reinterpret_cast<uint32_t*>(epi_patch), p.out_lo + off, p.m, rows_valid, lane);
           }
         }
       }
@@ -618,7 +662,8 @@ static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w
   p.a_plane_bytes = tc::BLOCK_M * tc::BLOCK_K * 2;
   p.b_plane_bytes = static_cast<uint32_t>(p.block_n) * tc::BLOCK_K * 2;
   p.stage_bytes = static_cast<uint32_t>(passes == 3 ? 2 : 1) * (p.a_plane_bytes + p.b_plane_bytes);
-  const int budget = tc::SMEM_LIMIT - 2048;
+  const int epi_bytes = 8 * tc::EPI_PATCH_WORDS * static_cast<int>(sizeof(float));  // 8 epilogue warps
+  const int budget = tc::SMEM_LIMIT - 1024 - epi_bytes;
   p.stages = budget / static_cast<int>(p.stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (p.stages < 2) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: tile does not fit shared memory");
@@ -638,7 +683,7 @@ static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w
     if ((st = tc::make_map(&mb_lo, passes == 3 ? w_lo : w_hi, k, m, tc::BLOCK_K)) != MRI_OK) return st;
   }
 
-  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024;
+  const size_t smem = static_cast<size_t>(p.stages) * p.stage_bytes + 1024 + epi_bytes;
   MRI_CUDA_OK(cudaFuncSetAttribute(tc::siren_tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
