@@ -153,6 +153,29 @@ int mri_siren_tc_wgrad(const void* g_hi, const void* g_lo, const void* x_hi, con
 /* (hi, lo) bf16 planes of a * b (b may be NULL): dPre = dOut * act' at the head of the backward pass. */
 int mri_siren_tc_mul_split(const float* a, const float* b, int64_t count, void* hi, void* lo, void* stream);
 
+/* First layer of a wide SIREN (K = dim_in <= 4): planes of sin(w0 (x W0^T + b0)) written directly in the bf16
+ * (hi, lo) format the tensor-core layers read; aux (optional) = w0 cos(.) for the backward pass. */
+int mri_siren_first_forward(const float* x, int64_t ldx, const float* w, const float* b, int64_t n, int dim_in,
+                            int h, float w0, void* out_hi, void* out_lo, float* aux, void* stream);
+
+/* Backward of the first layer's parameters from dPre0 (n, h) fp32: grad_w0 (h, dim_in) += dPre0^T x,
+ * grad_b0 (h) += column sums (grad_b0 may be NULL). */
+int mri_siren_first_backward(const float* dpre0, const float* x, int64_t ldx, int64_t n, int dim_in, int h,
+                             float* grad_w0, float* grad_b0, void* stream);
+
+/* Output layer (dim_out <= 4, identity activation) straight from the last hidden layer's planes:
+ * y (n, m_out) = (hi + lo) W_last^T + b_last. */
+int mri_siren_last_forward(const void* hi, const void* lo, const float* w, const float* b, int64_t n, int h,
+                           int m_out, float* y, void* stream);
+
+/* Backward of the output layer fused with the head of the hidden backward:
+ *   dPre (n, h) = (grad_y W_last) * aux  -> (dpre_hi, dpre_lo) planes;  grad_b_hidden (h) += column sums of dPre
+ *   grad_w_last (m_out, h) += grad_y^T (act_hi + act_lo);  grad_b_last (m_out) += column sums of grad_y
+ * grad_b_hidden / grad_b_last may be NULL. */
+int mri_siren_last_backward(const float* grad_y, const float* w, const float* aux, const void* act_hi,
+                            const void* act_lo, int64_t n, int h, int m_out, void* dpre_hi, void* dpre_lo,
+                            float* grad_b_hidden, float* grad_w_last, float* grad_b_last, void* stream);
+
 /* ---- loss / optimiser ------------------------------------------------------------------ */
 
 /* F.mse_loss(y, y_pred) (models.py:64): *loss += sum((pred-target)^2) * inv_count and

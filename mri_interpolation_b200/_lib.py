@@ -63,6 +63,10 @@ SIGNATURES = {
     "mri_siren_tc_dgrad": [_P, _P, _P, _P, _I64, _I, _I, _I, _P, _P, _P, _P, _P],
     "mri_siren_tc_wgrad": [_P, _P, _P, _P, _I64, _I, _I, _I, _P, _P, _P],
     "mri_siren_tc_mul_split": [_P, _P, _I64, _P, _P, _P],
+    "mri_siren_first_forward": [_P, _I64, _P, _P, _I64, _I, _I, _F, _P, _P, _P, _P],
+    "mri_siren_first_backward": [_P, _P, _I64, _I64, _I, _I, _P, _P, _P],
+    "mri_siren_last_forward": [_P, _P, _P, _P, _I64, _I, _I, _P, _P],
+    "mri_siren_last_backward": [_P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _P, _P],
 }
 _SPECIAL = {
     "mri_version": ([], _I),

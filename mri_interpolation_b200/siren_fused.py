@@ -37,6 +37,8 @@ def eligible(net) -> bool:
             if not (tc.supported(k, m) and tc.supported(m, k) and tc.wgrad_supported(k, m)):
                 return False
     last = net.last_layer
+    if layers[0].weight.shape[1] > 4 or last.weight.shape[0] > 4:
+        return False  # first/last-layer stream kernels cover dim_in <= 4, dim_out <= 4
     return isinstance(last.activation, torch.nn.Identity) and last.bias is not None
 
 
@@ -51,83 +53,81 @@ class SirenTcFn(torch.autograd.Function):
         n = x2.shape[0]
         dev = x.device
         train = any(p.requires_grad for p in params)
-        h_dim = ws[0].shape[0]
-        # layer 0 on the CUDA cores
-        h0 = torch.empty((n, h_dim), device=dev, dtype=torch.float32)
-        pre0 = torch.empty_like(h0) if train else None
-        _lib.call("mri_dense_forward", x2.data_ptr(), x2.stride(0), ws[0].data_ptr(), bs[0].data_ptr(), n, x2.shape[1],
-                  h_dim, ACT_SINE, float(w0s[0]), h0.data_ptr(), _lib.ptr(pre0), _lib.stream())
-        a_hi, a_lo = tc.split(h0, need_lo=(passes == 3))
-        del h0
-        acts = [(a_hi, a_lo)]  # acts[i] = input planes of layer i+1
-        auxs: List[Optional[torch.Tensor]] = [None]
+        h_dim, d_in = ws[0].shape
+        m_out = ws[-1].shape[0]
+        if d_in > 4 or m_out > 4:
+            raise MriB200Error("tensor-core SIREN path handles dim_in <= 4 and dim_out <= 4; use precision='fp32'")
+        three = passes == 3
+        # first layer (K = dim_in): planes written directly, no fp32 activations, no split pass
+        a_hi = torch.empty((n, h_dim), device=dev, dtype=torch.bfloat16)
+        a_lo = torch.empty_like(a_hi) if three else None
+        aux0 = torch.empty((n, h_dim), device=dev, dtype=torch.float32) if train else None
+        _lib.call("mri_siren_first_forward", x2.data_ptr(), x2.stride(0), ws[0].data_ptr(), bs[0].data_ptr(), n, d_in, h_dim,
+                  float(w0s[0]), a_hi.data_ptr(), _lib.ptr(a_lo), _lib.ptr(aux0), _lib.stream())
+        acts = [(a_hi, a_lo)]  # acts[i] = output planes of layer i = input of layer i+1
+        auxs: List[Optional[torch.Tensor]] = [aux0]
         wplanes = [None]
-        last_f32 = None
         for i in range(1, n_hidden):
-            w_hi, w_lo = tc.split(ws[i], need_lo=(passes == 3))  # weights change every optimiser step: re-split
+            w_hi, w_lo = tc.split(ws[i], need_lo=three)  # weights change every optimiser step: re-split
             wplanes.append((w_hi, w_lo))
-            is_last_hidden = i == n_hidden - 1
-            oh, ol, of, aux = tc.layer(acts[-1][0], acts[-1][1], w_hi, w_lo, bs[i], ACT_SINE, w0s[i], passes=passes,
-                                       want_planes=(not is_last_hidden) or train, want_f32=is_last_hidden, want_aux=train)
+            oh, ol, _, aux = tc.layer(acts[-1][0], acts[-1][1], w_hi, w_lo, bs[i], ACT_SINE, w0s[i], passes=passes,
+                                      want_planes=True, want_f32=False, want_aux=train)
             acts.append((oh, ol))
             auxs.append(aux)
-            if is_last_hidden:
-                last_f32 = of
             if not train:
                 acts = acts[-1:]
-        m_out = ws[-1].shape[0]
         y = torch.empty((n, m_out), device=dev, dtype=torch.float32)
-        _lib.call("mri_dense_forward", last_f32.data_ptr(), last_f32.stride(0), ws[-1].data_ptr(), bs[-1].data_ptr(), n,
-                  h_dim, m_out, ACT_IDENTITY, 1.0, y.data_ptr(), None, _lib.stream())
+        _lib.call("mri_siren_last_forward", acts[-1][0].data_ptr(), _lib.ptr(acts[-1][1]), ws[-1].data_ptr(), bs[-1].data_ptr(), n,
+                  h_dim, m_out, y.data_ptr(), _lib.stream())
         if train:
-            ctx.saved = (x2, pre0, acts, auxs, last_f32, wplanes)
+            ctx.saved = (x2, acts, auxs, wplanes)
             ctx.params = params
             ctx.w0s, ctx.passes = w0s, passes
         ctx.train = train
+        ctx.n_params = len(params)
         return y.reshape(*lead, m_out)
 
     @staticmethod
     def backward(ctx, grad_y):
         if not ctx.train:
-            return (None,) * (3 + len(ctx.params))
-        x2, pre0, acts, auxs, last_f32, wplanes = ctx.saved
+            return (None,) * (3 + ctx.n_params)
+        x2, acts, auxs, wplanes = ctx.saved
         params, w0s, passes = ctx.params, ctx.w0s, ctx.passes
         ws, bs = params[0::2], params[1::2]
         n_hidden = len(w0s)
         n = x2.shape[0]
         dev = x2.device
-        h_dim = ws[0].shape[0]
+        h_dim, d_in = ws[0].shape
         m_out = ws[-1].shape[0]
-        grads = []
-        direct = []
+        three = passes == 3
+        grads, direct = [], []
         for p in params:
             d = Fn._direct_grad(p)
             direct.append(d is not None)
             grads.append(d if d is not None else torch.zeros_like(p))
         gw, gb = grads[0::2], grads[1::2]
         gy = grad_y.reshape(n, m_out).contiguous()
-        # last layer (identity): dH = gy W_last ; dW_last += gy^T h ; db_last += colsum(gy)
-        dpre_scratch = torch.empty_like(gy)
-        dh = torch.empty((n, h_dim), device=dev, dtype=torch.float32)
-        _lib.call("mri_dense_backward", last_f32.data_ptr(), last_f32.stride(0), ws[-1].data_ptr(), None, gy.data_ptr(), n,
-                  h_dim, m_out, ACT_IDENTITY, 1.0, dpre_scratch.data_ptr(), dh.data_ptr(), gw[-1].data_ptr(),
-                  gb[-1].data_ptr(), _lib.stream(), kernels=3)
-        g_hi, g_lo = tc.mul_split(dh, auxs[n_hidden - 1], need_lo=(passes == 3))
-        del dh
-        dh0 = None
-        for i in range(n_hidden - 1, 0, -1):
+        last = n_hidden - 1
+        # output layer + head of the hidden backward in one pass over (n, H):
+        #   dPre_last = (gy W_out) * aux_last -> planes; db_last_hidden; dW_out = gy^T h; db_out
+        g_hi = torch.empty((n, h_dim), device=dev, dtype=torch.bfloat16)
+        g_lo = torch.empty_like(g_hi) if three else None
+        _lib.call("mri_siren_last_backward", gy.data_ptr(), ws[-1].data_ptr(), auxs[last].data_ptr(), acts[last][0].data_ptr(),
+                  _lib.ptr(acts[last][1]), n, h_dim, m_out, g_hi.data_ptr(), _lib.ptr(g_lo), gb[last].data_ptr(),
+                  gw[-1].data_ptr(), gb[-1].data_ptr(), _lib.stream(), kernels=3)
+        dpre0 = None
+        for i in range(last, 0, -1):
             x_hi, x_lo = acts[i - 1]
-            tc.wgrad(g_hi, g_lo, x_hi, x_lo, gw[i], gb[i], passes=passes)
+            tc.wgrad(g_hi, g_lo, x_hi, x_lo, gw[i], gb[i] if i != last else None, passes=passes)
             w_hi, w_lo = wplanes[i]  # the forward's planes, read as an MN-major operand: no transpose
             if i > 1:
                 g_hi, g_lo, _ = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[i - 1], want_planes=True)
             else:
-                _, _, dh0 = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, want_planes=False, want_f32=True)
-        # layer 0 (CUDA cores): dpre0 = dh0 * w0 cos(w0 pre0); dW0, db0
-        scratch = torch.empty_like(dh0)
-        _lib.call("mri_dense_backward", x2.data_ptr(), x2.stride(0), ws[0].data_ptr(), pre0.data_ptr(), dh0.data_ptr(), n,
-                  x2.shape[1], h_dim, ACT_SINE, float(w0s[0]), scratch.data_ptr(), None, gw[0].data_ptr(), gb[0].data_ptr(),
-                  _lib.stream(), kernels=2)
+                _, _, dpre0 = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[0], want_planes=False, want_f32=True)
+        if n_hidden == 1:
+            raise MriB200Error("tensor-core SIREN path needs at least two sine layers")
+        _lib.call("mri_siren_first_backward", dpre0.data_ptr(), x2.data_ptr(), x2.stride(0), n, d_in, h_dim, gw[0].data_ptr(),
+                  gb[0].data_ptr(), _lib.stream())
         out = [None if d else g for d, g in zip(direct, grads)]
         return (None, None, None) + tuple(out)
 
