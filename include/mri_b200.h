@@ -138,10 +138,11 @@ int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void* w_hi, con
 
 /* Input gradient of the layer above (autograd of models.py:153-156): dX (n, k) = G (n, m) . W (m, k), with W's
  * planes exactly as the forward uses them (no transpose: W is read as an MN-major tensor-core operand);
- * optional "* mul" (n, k) = the previous layer's activation derivative, so the result is that layer's dPre. */
+ * optional "* mul" (n, k) = the previous layer's activation derivative, so the result is that layer's dPre;
+ * colsum (k) or NULL += column sums of the result = that layer's bias gradient (no separate reduction pass). */
 int mri_siren_tc_dgrad(const void* g_hi, const void* g_lo, const void* w_hi, const void* w_lo, int64_t n,
                        int k, int m, int passes, const float* mul, void* out_hi, void* out_lo,
-                       float* out_f32, void* stream);
+                       float* out_f32, float* colsum, void* stream);
 
 /* Weight/bias gradient of the layer above on the tensor cores (autograd of models.py:153-156):
  *   grad_w[j, i] += sum_n G[n, j] X[n, i]   G = dPre planes (n, m), X = layer-input planes (n, k)

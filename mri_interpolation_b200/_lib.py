@@ -60,7 +60,7 @@ SIGNATURES = {
     "mri_siren_tc_supported": [_I, _I],
     "mri_siren_tc_split": [_P, _I64, _P, _P, _P],
     "mri_siren_tc_layer": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
-    "mri_siren_tc_dgrad": [_P, _P, _P, _P, _I64, _I, _I, _I, _P, _P, _P, _P, _P],
+    "mri_siren_tc_dgrad": [_P, _P, _P, _P, _I64, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "mri_siren_tc_wgrad": [_P, _P, _P, _P, _I64, _I, _I, _I, _P, _P, _P],
     "mri_siren_tc_mul_split": [_P, _P, _I64, _P, _P, _P],
     "mri_siren_first_forward": [_P, _I64, _P, _P, _I64, _I, _I, _F, _P, _P, _P, _P],

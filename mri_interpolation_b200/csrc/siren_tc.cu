@@ -44,6 +44,7 @@ struct LayerParams {
   __nv_bfloat16* out_lo;   // (n_rows, m) or null
   float* out_f32;          // (n_rows, m) or null
   float* aux_f32;          // (n_rows, m) or null: w0*cos(w0*pre) for the backward pass
+  float* colsum;           // (m) or null: += column sums of the final `out` (bias gradient when out = dPre)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -370,6 +371,15 @@ siren_tc_layer_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
             for (int j = 0; j < 32; ++j) out[j] *= f[j];
           }
           if (p.out_f32) store_tile_f32(out, epi_patch, p.out_f32 + off, p.m, rows_valid, lane);
+          if (p.colsum) {  // bias gradient: column sums of this 32 x 32 patch, one atomic per column
+#pragma unroll
+            for (int j = 0; j < 32; ++j) epi_patch[lane * 33 + j] = out[j];
+            __syncwarp();
+            float cs = 0.0f;
+            for (int r = 0; r < rows_valid; ++r) cs += epi_patch[r * 33 + lane];
+            red_add_f32(p.colsum + col0 + lane, cs);
+            __syncwarp();
+          }
           if (p.out_hi) {
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -644,7 +654,7 @@ extern "C" int mri_siren_tc_split(const float* src, int64_t count, void* hi, voi
 
 static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                                int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
-                               void* out_lo, float* out_f32, float* aux_f32, int b_mn_major, void* stream) {
+                               void* out_lo, float* out_f32, float* aux_f32, int b_mn_major, float* colsum, void* stream) {
   if (!a_hi || !w_hi) return fail(MRI_ERR_INVALID, "siren_tc_layer: null operand");
   if (passes != 1 && passes != 3) return fail(MRI_ERR_INVALID, "siren_tc_layer: passes must be 1 (bf16) or 3 (split fp32)");
   if (passes == 3 && (!a_lo || !w_lo)) return fail(MRI_ERR_INVALID, "siren_tc_layer: lo planes required for passes=3");
@@ -652,7 +662,7 @@ static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w
   if (act != MRI_ACT_IDENTITY && act != MRI_ACT_SINE) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: activation %d", act);
   if (n < 0) return fail(MRI_ERR_INVALID, "siren_tc_layer: negative n");
   if (n == 0) return MRI_OK;
-  if (!out_hi && !out_f32) return fail(MRI_ERR_INVALID, "siren_tc_layer: no output requested");
+  if (!out_hi && !out_f32 && !colsum) return fail(MRI_ERR_INVALID, "siren_tc_layer: no output requested");
 
   tc::LayerParams p{};
   p.n_rows = n; p.k = k; p.m = m; p.passes = passes; p.act = act; p.w0 = w0; p.b_mn_major = b_mn_major;
@@ -669,7 +679,7 @@ static int siren_tc_layer_impl(const void* a_hi, const void* a_lo, const void* w
   if (p.stages < 2) return fail(MRI_ERR_UNSUPPORTED, "siren_tc_layer: tile does not fit shared memory");
   p.bias = bias; p.mul = mul;
   p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo);
-  p.out_f32 = out_f32; p.aux_f32 = aux_f32;
+  p.out_f32 = out_f32; p.aux_f32 = aux_f32; p.colsum = colsum;
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int st;
@@ -762,13 +772,13 @@ extern "C" int mri_siren_tc_layer(const void* a_hi, const void* a_lo, const void
                                   int64_t n, int k, int m, int act, float w0, int passes, const float* mul, void* out_hi,
                                   void* out_lo, float* out_f32, float* aux_f32, void* stream) {
   return siren_tc_layer_impl(a_hi, a_lo, w_hi, w_lo, bias, n, k, m, act, w0, passes, mul, out_hi, out_lo, out_f32, aux_f32, 0,
-                             stream);
+                             nullptr, stream);
 }
 
 extern "C" int mri_siren_tc_dgrad(const void* g_hi, const void* g_lo, const void* w_hi, const void* w_lo, int64_t n, int k,
                                   int m, int passes, const float* mul, void* out_hi, void* out_lo, float* out_f32,
-                                  void* stream) {
+                                  float* colsum, void* stream) {
   // dX (n, k) = G (n, m) . W (m, k): W is consumed as stored (rows = the GEMM's K), i.e. as an MN-major B operand
   return siren_tc_layer_impl(g_hi, g_lo, w_hi, w_lo, nullptr, n, /*gemm K=*/m, /*gemm N=*/k, MRI_ACT_IDENTITY, 1.0f, passes, mul,
-                             out_hi, out_lo, out_f32, nullptr, 1, stream);
+                             out_hi, out_lo, out_f32, nullptr, 1, colsum, stream);
 }

@@ -118,16 +118,17 @@ class SirenTcFn(torch.autograd.Function):
         dpre0 = None
         for i in range(last, 0, -1):
             x_hi, x_lo = acts[i - 1]
-            tc.wgrad(g_hi, g_lo, x_hi, x_lo, gw[i], gb[i] if i != last else None, passes=passes)
+            tc.wgrad(g_hi, g_lo, x_hi, x_lo, gw[i], None, passes=passes)  # bias gradients come from the epilogues
             w_hi, w_lo = wplanes[i]  # the forward's planes, read as an MN-major operand: no transpose
             if i > 1:
-                g_hi, g_lo, _ = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[i - 1], want_planes=True)
+                g_hi, g_lo, _ = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[i - 1], want_planes=True,
+                                         colsum=gb[i - 1])
             else:
                 _, _, dpre0 = tc.dgrad(g_hi, g_lo, w_hi, w_lo, passes=passes, mul=auxs[0], want_planes=False, want_f32=True)
         if n_hidden == 1:
             raise MriB200Error("tensor-core SIREN path needs at least two sine layers")
         _lib.call("mri_siren_first_backward", dpre0.data_ptr(), x2.data_ptr(), x2.stride(0), n, d_in, h_dim, gw[0].data_ptr(),
-                  gb[0].data_ptr(), _lib.stream())
+                  gb[0].data_ptr(), _lib.stream())  # dW0 and db0 in one pass over dPre0
         out = [None if d else g for d, g in zip(direct, grads)]
         return (None, None, None) + tuple(out)
 

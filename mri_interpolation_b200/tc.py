@@ -74,8 +74,10 @@ def wgrad(g_hi, g_lo, x_hi, x_lo, grad_w: torch.Tensor, grad_b: Optional[torch.T
               grad_w.data_ptr(), _lib.ptr(grad_b), _lib.stream(), kernels=2 if grad_b is not None else 1)
 
 
-def dgrad(g_hi, g_lo, w_hi, w_lo, passes: int = 3, mul=None, want_planes: bool = True, want_f32: bool = False):
-    """dX (n, k) = G (n, m) . W (m, k) [* mul] with W's planes as the forward uses them (no transpose)."""
+def dgrad(g_hi, g_lo, w_hi, w_lo, passes: int = 3, mul=None, want_planes: bool = True, want_f32: bool = False,
+          colsum: Optional[torch.Tensor] = None):
+    """dX (n, k) = G (n, m) . W (m, k) [* mul] with W's planes as the forward uses them (no transpose);
+    ``colsum`` (k,) is incremented by the column sums of the result (bias gradient of the previous layer)."""
     n, m = g_hi.shape
     if w_hi.shape[0] != m:
         raise MriB200Error(f"tc.dgrad: G is (n,{m}) but W is {tuple(w_hi.shape)}")
@@ -85,5 +87,5 @@ def dgrad(g_hi, g_lo, w_hi, w_lo, passes: int = 3, mul=None, want_planes: bool =
     out_lo = torch.empty((n, k), device=dev, dtype=torch.bfloat16) if (want_planes and passes == 3) else None
     out_f32 = torch.empty((n, k), device=dev, dtype=torch.float32) if want_f32 else None
     _lib.call("mri_siren_tc_dgrad", g_hi.data_ptr(), _lib.ptr(g_lo), w_hi.data_ptr(), _lib.ptr(w_lo), n, k, m, int(passes),
-              _lib.ptr(mul), _lib.ptr(out_hi), _lib.ptr(out_lo), _lib.ptr(out_f32), _lib.stream())
+              _lib.ptr(mul), _lib.ptr(out_hi), _lib.ptr(out_lo), _lib.ptr(out_f32), _lib.ptr(colsum), _lib.stream())
     return out_hi, out_lo, out_f32

@@ -143,9 +143,11 @@ def test_tc_dgrad_on_untransposed_weights(n, k, m, passes):
     mul = torch.randn(n, k, device=DEV, generator=gen)
     g_hi, g_lo = tc.split(g)
     w_hi, w_lo = tc.split(w)
+    cs = torch.zeros(k, device=DEV)
     oh, ol, of = tc.dgrad(g_hi, g_lo if passes == 3 else None, w_hi, w_lo if passes == 3 else None, passes=passes, mul=mul,
-                          want_f32=True)
+                          want_f32=True, colsum=cs)
     ref = (g.double() @ w.double()) * mul.double()
+    assert rel_err(cs, of.double().sum(0)) < 1e-4
     assert rel_err(of, ref) < (3e-5 if passes == 3 else 8e-3)
     if passes == 3:
         assert rel_err(oh.float() + ol.float(), ref) < 5e-5
