@@ -328,8 +328,13 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     inflight = []
+    trace = [] if os.environ.get("MRI_BENCH_TRACE") == "1" else None
     for i in range(args.warmup, total_steps):
         loss = step(i)
+        if trace is not None:
+            te = torch.cuda.Event(enable_timing=True)
+            te.record()
+            trace.append(te)
         # bound the host's run-ahead to two steps (a saturated launch queue starves NCCL's progress thread and made
         # multi-GPU SIREN steps ~25% slower); the GPU stays fed: the event waited on is two steps old
         ev = torch.cuda.Event()
@@ -341,6 +346,8 @@ def main():
     barrier()
     launches = _lib.launch_count - launches0
     ms = ev0.elapsed_time(ev1)
+    if trace:
+        sys.stderr.write("per-step ms: " + " ".join(f"{a.elapsed_time(b):.1f}" for a, b in zip([ev0] + trace[:-1], trace)) + "\n")
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
