@@ -193,6 +193,17 @@ int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t
                   double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                   int zero_grad, void* stream);
 
+/* Data-parallel variant of the step above, ONE kernel per rank over NVLink peer memory: for its shard
+ * [shard_begin, shard_begin + shard_len) of the flat arena the rank sums the gradients of all `world` ranks by
+ * loading their gradient arenas directly (host_peer_grads[r] = device pointer of rank r's arena, P2P-mapped, e.g.
+ * torch symmetric memory), applies Adam with its local moment shards and stores the new parameters into every
+ * rank's parameter arena (host_peer_params[r]).  = reduce-scatter + Adam + all-gather fused; the caller brackets it
+ * with cross-rank barriers (gradients complete before, parameters visible after).  grad_scale = 1/world for means. */
+int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, int world, int rank,
+                          float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
+                          double lr, double beta1, double beta2, double eps, double weight_decay,
+                          double grad_scale, void* stream);
+
 /* ---- dense-grid sweep -------------------------------------------------------------------- */
 
 /* Coordinates of voxels [first, first+count) of a C-order grid of `shape` (launcher.py:191-202,

@@ -9,6 +9,8 @@ gradient over the ranks with a single NCCL all-reduce (NVLink 5 / NVSwitch) righ
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Iterable, List, Optional
 
 import torch
@@ -25,7 +27,9 @@ class FlatArena:
     """Re-homes a list of parameters into one flat fp32 buffer (and their gradients into another),
     keeping every ``nn.Parameter`` object - hence every state_dict key and shape - unchanged."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], symmetric_group=None, pad_to: int = _ALIGN):
+        """``symmetric_group``: allocate both arenas as torch symmetric memory of that process group so that
+        every rank can load/store every other rank's arena over NVLink (peer pointers in ``data_hdl.buffer_ptrs``)."""
         self.params: List[torch.nn.Parameter] = [p for p in params]
         if not self.params:
             raise MriB200Error("FlatArena: no parameters")
@@ -41,9 +45,20 @@ class FlatArena:
         for p in self.params:
             self.offsets.append(total)
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        total = (total + pad_to - 1) // pad_to * pad_to
         self.numel = total
-        self.data = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.data_hdl = self.grad_hdl = None
+        if symmetric_group is not None:
+            import torch.distributed._symmetric_memory as symm
+            self.data = symm.empty(total, dtype=torch.float32, device=dev)
+            self.grad = symm.empty(total, dtype=torch.float32, device=dev)
+            self.data.zero_()
+            self.grad.zero_()
+            self.data_hdl = symm.rendezvous(self.data, symmetric_group)
+            self.grad_hdl = symm.rendezvous(self.grad, symmetric_group)
+        else:
+            self.data = torch.zeros(total, device=dev, dtype=torch.float32)
+            self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
         with torch.no_grad():
             for p, off in zip(self.params, self.offsets):
                 view = self.data[off:off + p.numel()].view(p.shape)
@@ -85,18 +100,41 @@ class FusedAdam(torch.optim.Optimizer):
     """
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 process_group=None, grad_average: bool = True, fuse_zero_grad: bool = True, data_parallel: bool = True):
+                 process_group=None, grad_average: bool = True, fuse_zero_grad: bool = True, data_parallel: bool = True,
+                 sharded: Optional[bool] = None):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
             raise MriB200Error("FusedAdam handles a single parameter group (the reference uses one)")
         plist = [p for p in self.param_groups[0]["params"] if p.requires_grad]
-        self.arena = FlatArena(plist)
-        self.exp_avg = torch.zeros_like(self.arena.data)
-        self.exp_avg_sq = torch.zeros_like(self.arena.data)
-        self.step_count = 0
         self.process_group = process_group
         self.data_parallel = data_parallel  # False: never all-reduce, even when torch.distributed is initialised
+        world = self._world()
+        if sharded is None:
+            sharded = os.environ.get("MRI_DP_SHARDED", "1") == "1"
+        self.sharded = False
+        if sharded and world > 1:
+            # fused reduce-scatter + Adam + all-gather over NVLink peer memory (csrc/optim.cu::adam_sharded_kernel)
+            try:
+                group = process_group if process_group is not None else dist.group.WORLD
+                self.arena = FlatArena(plist, symmetric_group=group, pad_to=4 * world)
+                self.sharded = True
+            except Exception as e:  # noqa: BLE001 - no P2P / symmetric memory on this box: NCCL all-reduce path
+                import warnings
+                warnings.warn(f"symmetric-memory arena unavailable ({e}); falling back to the NCCL all-reduce + full Adam step")
+        if not self.sharded:
+            self.arena = FlatArena(plist)
+        if self.sharded:
+            self.shard_len = self.arena.numel // world
+            self.shard_begin = self.shard_len * dist.get_rank(self.process_group)
+            self.exp_avg = torch.zeros(self.shard_len, device=self.arena.data.device, dtype=torch.float32)
+            self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+            self._peer_grads = (ctypes.c_uint64 * world)(*[int(p) for p in self.arena.grad_hdl.buffer_ptrs])
+            self._peer_params = (ctypes.c_uint64 * world)(*[int(p) for p in self.arena.data_hdl.buffer_ptrs])
+        else:
+            self.exp_avg = torch.zeros_like(self.arena.data)
+            self.exp_avg_sq = torch.zeros_like(self.arena.data)
+        self.step_count = 0
         self.grad_average = grad_average
         self.fuse_zero_grad = fuse_zero_grad
         self._grads_clean = True  # freshly allocated arena gradient is zero
@@ -133,7 +171,7 @@ class FusedAdam(torch.optim.Optimizer):
         """Bucket the table gradients per level group: group g's all-reduce runs on a side stream while the
         scatter kernel of group g+1 executes; the (small) non-table gradients go first.  Requires exactly one
         backward per step.  Returns False (and stays on the single all-reduce) when not applicable."""
-        if self._world() == 1:
+        if self._world() == 1 or self.sharded:
             return False
         tables = encoder.tables()
         index = {id(p): i for i, p in enumerate(self.arena.params)}
@@ -189,8 +227,23 @@ class FusedAdam(torch.optim.Optimizer):
             if not self.arena.intact():
                 raise MriB200Error("FusedAdam: parameters no longer alias the flat arena (was the model moved "
                                    "after configure_optimizers()?)")
-        scale = self.sync_gradients()
         g = self.param_groups[0]
+        if self.sharded and self._world() > 1:
+            world = self._world()
+            self.step_count += 1
+            self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
+            _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, world, dist.get_rank(self.process_group),
+                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
+                      float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                      (1.0 / world) if self.grad_average else 1.0, _lib.stream())
+            self.arena.data_hdl.barrier(channel=1)  # new parameters landed everywhere; peers are done reading my gradients
+            self.arena.grad.zero_()
+            self.allreduce_count += 1
+            self._grads_clean = True
+            return loss
+        if self.sharded:
+            raise MriB200Error("FusedAdam: a sharded optimiser cannot step with data_parallel switched off")
+        scale = self.sync_gradients()
         self.step_count += 1
         _lib.call("mri_adam_step", self.arena.data.data_ptr(), self.arena.grad.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), self.arena.numel, self.step_count, float(g["lr"]), float(g["betas"][0]),

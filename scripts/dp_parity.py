@@ -23,7 +23,7 @@ steps, n_global = 8, 1 << 16
 torch.manual_seed(1337)
 dp_model = models.HashMLP(**kw).to(dev)
 dp_opt = dp_model.configure_optimizers()
-overlap = os.environ.get("MRI_DP_OVERLAP", "1") == "1" and dp_opt.enable_overlap(dp_model.encoder, n_groups=3)
+overlap = (not dp_opt.sharded) and os.environ.get("MRI_DP_OVERLAP", "1") == "1" and dp_opt.enable_overlap(dp_model.encoder, n_groups=3)
 torch.manual_seed(1337)
 ref_model = models.HashMLP(**kw).to(dev)
 ref_opt = FusedAdam(ref_model.parameters(), lr=5e-3, data_parallel=False)
@@ -42,6 +42,7 @@ for (k, a), (_, b) in zip(dp_model.state_dict().items(), ref_model.state_dict().
         worst = max(worst, float((a - b).norm() / b.norm()))
 # replicas identical across ranks
 flat = dp_opt.arena.data.clone()
+torch.cuda.synchronize()
 ref0 = flat.clone()
 dist.broadcast(ref0, 0)
 replica_diff = float((flat - ref0).abs().max())
@@ -54,7 +55,7 @@ if rank == 0:
     single = sweep.dense_sweep(dp_model, shape).reshape(shape).cpu().numpy()
     ok_sweep = bool((single == full).all())
 res = {"world": world, "steps": steps, "global_batch": n_global, "max_rel_param_diff_vs_single_gpu": worst,
-       "max_abs_replica_diff": replica_diff, "allreduces": dp_opt.allreduce_count, "overlap": bool(overlap), "sweep_slabs_tile_exactly": ok_sweep}
+       "max_abs_replica_diff": replica_diff, "allreduces": dp_opt.allreduce_count, "overlap": bool(overlap), "sharded_p2p_adam": bool(dp_opt.sharded), "sweep_slabs_tile_exactly": ok_sweep}
 if rank == 0:
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
