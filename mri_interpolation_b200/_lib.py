@@ -50,7 +50,8 @@ SIGNATURES = {
     "mri_dense_backward": [_P, _I64, _P, _P, _P, _I64, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "mri_mse_loss_grad": [_P, _P, _I64, _F, _P, _P, _P],
     "mri_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _I, _P],
-    "mri_adam_step_sharded": [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), _I, _I, _P, _P, _I64, _I64, _I64,
+    "mri_adam_step_sharded": [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_uint64,
+                              _I, _I, _P, _P, _I64, _I64, _I64,
                               _D, _D, _D, _D, _D, _D, _P],
     "mri_grid_coords": [_P, ctypes.POINTER(ctypes.c_int32), _I, _I64, _I64, _P, _P],
     "mri_gather_voxels": [_P, ctypes.POINTER(ctypes.c_int32), _I, _P, _I64, _P, _P, _P, _P],

@@ -85,7 +85,22 @@ constexpr int MAX_PEERS = 8;
 struct PeerPtrs {
   const float* grad[MAX_PEERS];
   float* param[MAX_PEERS];
+  const float* grad_mc;  // NVSwitch multicast mapping of the gradient arenas (0 = not available)
+  float* param_mc;       // NVSwitch multicast mapping of the parameter arenas
 };
+
+// in-switch (NVLS) reduction: one load returns the sum over every rank's copy of the address
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc_addr) : "memory");
+  return r;
+}
+// multicast store: the switch writes the value into every rank's copy
+__device__ __forceinline__ void multimem_st(float* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers, int world, int rank, float* __restrict__ m,
                                                            float* __restrict__ v, int64_t shard_begin4, int64_t shard_len4,
@@ -94,11 +109,15 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < shard_len4; i += stride) {
     const int64_t gi = shard_begin4 + i;  // float4 index inside the arena
     float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (peers.grad_mc) {
+      gg = multimem_ld_reduce_add(peers.grad_mc + 4 * gi);
+    } else {
 #pragma unroll
-    for (int r = 0; r < MAX_PEERS; ++r) {
-      if (r < world) {
-        const float4 t = reinterpret_cast<const float4*>(peers.grad[r])[gi];
-        gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+      for (int r = 0; r < MAX_PEERS; ++r) {
+        if (r < world) {
+          const float4 t = reinterpret_cast<const float4*>(peers.grad[r])[gi];
+          gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+        }
       }
     }
     float4 pp = reinterpret_cast<const float4*>(peers.param[rank])[gi];
@@ -112,9 +131,13 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
     adam_update(pp.w, gg.w, mm.w, vv.w, b);
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (peers.param_mc) {
+      multimem_st(peers.param_mc + 4 * gi, pp);
+    } else {
 #pragma unroll
-    for (int r = 0; r < MAX_PEERS; ++r)
-      if (r < world) reinterpret_cast<float4*>(peers.param[r])[gi] = pp;
+      for (int r = 0; r < MAX_PEERS; ++r)
+        if (r < world) reinterpret_cast<float4*>(peers.param[r])[gi] = pp;
+    }
   }
 }
 
@@ -123,8 +146,8 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
 
 using namespace mri;
 
-extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, int world, int rank,
-                                     float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
+extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast,
+                                     uint64_t param_multicast, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
                                      double lr, double beta1, double beta2, double eps, double weight_decay,
                                      double grad_scale, void* stream) {
   if (!host_peer_grads || !host_peer_params || !m_shard || !v_shard) return fail(MRI_ERR_INVALID, "adam_sharded: null pointer");
@@ -138,6 +161,9 @@ extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint
     peers.grad[r] = reinterpret_cast<const float*>(host_peer_grads[r]);
     peers.param[r] = reinterpret_cast<float*>(host_peer_params[r]);
   }
+  if ((grad_multicast | param_multicast) & 15) return fail(MRI_ERR_INVALID, "adam_sharded: multicast pointers must be 16-byte aligned");
+  peers.grad_mc = reinterpret_cast<const float*>(grad_multicast);
+  peers.param_mc = reinterpret_cast<float*>(param_multicast);
   const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
   const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
   AdamArgs a;

@@ -131,6 +131,12 @@ class FusedAdam(torch.optim.Optimizer):
             self.exp_avg_sq = torch.zeros_like(self.exp_avg)
             self._peer_grads = (ctypes.c_uint64 * world)(*[int(p) for p in self.arena.grad_hdl.buffer_ptrs])
             self._peer_params = (ctypes.c_uint64 * world)(*[int(p) for p in self.arena.data_hdl.buffer_ptrs])
+            # NVSwitch multicast (NVLS) mappings when the fabric offers them: in-switch reduction + multicast store
+            use_mc = os.environ.get("MRI_DP_MULTIMEM", "1") == "1"
+            self._grad_mc = int(getattr(self.arena.grad_hdl, "multicast_ptr", 0) or 0) if use_mc else 0
+            self._param_mc = int(getattr(self.arena.data_hdl, "multicast_ptr", 0) or 0) if use_mc else 0
+            if not (self._grad_mc and self._param_mc):
+                self._grad_mc = self._param_mc = 0
         else:
             self.exp_avg = torch.zeros_like(self.arena.data)
             self.exp_avg_sq = torch.zeros_like(self.arena.data)
@@ -232,7 +238,8 @@ class FusedAdam(torch.optim.Optimizer):
             world = self._world()
             self.step_count += 1
             self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
-            _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, world, dist.get_rank(self.process_group),
+            _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc, world,
+                      dist.get_rank(self.process_group),
                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
                       float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
                       (1.0 / world) if self.grad_average else 1.0, _lib.stream())
