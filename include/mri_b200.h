@@ -200,11 +200,12 @@ int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t
  * rank's parameter arena (host_peer_params[r]).  = reduce-scatter + Adam + all-gather fused; the caller brackets it
  * with cross-rank barriers (gradients complete before, parameters visible after).  grad_scale = 1/world for means.
  * grad_multicast / param_multicast: NVSwitch multicast (NVLS) mappings of the two arenas, or 0; when given, the sum
- * is ONE multimem.ld_reduce (in-switch reduction) and the broadcast ONE multimem.st per 16 bytes. */
+ * is ONE multimem.ld_reduce (in-switch reduction) and the broadcast ONE multimem.st per 16 bytes.
+ * zero_grad != 0: the shard owner also clears its slice of every rank's gradient arena (no separate memset). */
 int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params,
                           uint64_t grad_multicast, uint64_t param_multicast, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
                           double lr, double beta1, double beta2, double eps, double weight_decay,
-                          double grad_scale, void* stream);
+                          double grad_scale, int zero_grad, void* stream);
 
 /* ---- dense-grid sweep -------------------------------------------------------------------- */
 

@@ -131,12 +131,17 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
     adam_update(pp.w, gg.w, mm.w, vv.w, b);
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     if (peers.param_mc) {
       multimem_st(peers.param_mc + 4 * gi, pp);
+      if (a.zero_grad) multimem_st(const_cast<float*>(peers.grad_mc) + 4 * gi, zero);  // clears this slice on every rank
     } else {
 #pragma unroll
       for (int r = 0; r < MAX_PEERS; ++r)
-        if (r < world) reinterpret_cast<float4*>(peers.param[r])[gi] = pp;
+        if (r < world) {
+          reinterpret_cast<float4*>(peers.param[r])[gi] = pp;
+          if (a.zero_grad) reinterpret_cast<float4*>(const_cast<float*>(peers.grad[r]))[gi] = zero;
+        }
     }
   }
 }
@@ -149,7 +154,7 @@ using namespace mri;
 extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast,
                                      uint64_t param_multicast, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
                                      double lr, double beta1, double beta2, double eps, double weight_decay,
-                                     double grad_scale, void* stream) {
+                                     double grad_scale, int zero_grad, void* stream) {
   if (!host_peer_grads || !host_peer_params || !m_shard || !v_shard) return fail(MRI_ERR_INVALID, "adam_sharded: null pointer");
   if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(MRI_ERR_UNSUPPORTED, "adam_sharded: world=%d rank=%d", world, rank);
   if (shard_begin < 0 || shard_len < 0 || (shard_begin & 3) || (shard_len & 3) || step < 1)
@@ -176,7 +181,7 @@ extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint
   a.eps = static_cast<float>(eps);
   a.weight_decay = static_cast<float>(weight_decay);
   a.grad_scale = static_cast<float>(grad_scale);
-  a.zero_grad = 0;
+  a.zero_grad = zero_grad;  // the owner of a slice clears it in EVERY rank's gradient arena after reducing it
   const int64_t n4 = shard_len / 4;
   int64_t want = (n4 + 255) / 256;
   const int64_t cap = 8LL * sm_count();
