@@ -244,9 +244,13 @@ class FusedAdam(torch.optim.Optimizer):
                       dist.get_rank(self.process_group),
                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
                       float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                      (1.0 / world) if self.grad_average else 1.0, 1, _lib.stream())
-            # new parameters landed everywhere, every slice of my gradient arena was reduced and cleared by its owner
+                      (1.0 / world) if self.grad_average else 1.0, 1 if self._grad_mc else 0, _lib.stream())
+            # new parameters landed everywhere and every slice of my gradient arena has been read by its owner
             self.arena.data_hdl.barrier(channel=1)
+            if not self._grad_mc:
+                # P2P-pointer mode: clearing remotely would double the NVLink stores (measured 1.265 vs 1.221 ms/step at
+                # W=2), so each rank clears its own arena; in multimem mode the owner's multicast store already did it
+                self.arena.grad.zero_()
             self.allreduce_count += 1
             self._grads_clean = True
             return loss
