@@ -236,3 +236,30 @@ def test_fused_decoder2_vs_torch(k0, h, act, n):
     assert rel_err(encd.grad, enc.grad) < tol
     for p, r in zip(ps, (l1.weight, l1.bias, l2.weight, l2.bias)):
         assert rel_err(p.grad, r.grad) < tol
+
+
+def test_sharded_adam_kernel_emulated_two_ranks_on_one_gpu():
+    """mri_adam_step_sharded with both 'ranks' living on this GPU (two gradient arenas, two parameter replicas,
+    launched one after the other - no kernel waits on another): every replica must end up with the Adam update of the
+    SUMMED gradient scaled by 1/world, exactly like the all-reduce path."""
+    import ctypes
+    from mri_interpolation_b200 import _lib
+    n, world = 8192, 2
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    p0 = torch.randn(n, device=DEV, generator=gen) * 0.1
+    params = [p0.clone() for _ in range(world)]
+    grads = [torch.randn(n, device=DEV, generator=gen) for _ in range(world)]
+    ref_p, ref_g = p0.clone(), (grads[0] + grads[1])
+    ref_m, ref_v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    _lib.call("mri_adam_step", ref_p.data_ptr(), ref_g.clone().data_ptr(), ref_m.data_ptr(), ref_v.data_ptr(), n, 1, 5e-3, 0.9, 0.999,
+              1e-8, 0.0, 1.0 / world, 0, _lib.stream())
+    shard = n // world
+    pg = (ctypes.c_uint64 * world)(*[g.data_ptr() for g in grads])
+    pp = (ctypes.c_uint64 * world)(*[p.data_ptr() for p in params])
+    for r in range(world):
+        m, v = torch.zeros(shard, device=DEV), torch.zeros(shard, device=DEV)
+        _lib.call("mri_adam_step_sharded", pg, pp, 0, 0, world, r, m.data_ptr(), v.data_ptr(), r * shard, shard, 1, 5e-3, 0.9, 0.999,
+                  1e-8, 0.0, 1.0 / world, 0, _lib.stream())
+    for p in params:
+        torch.testing.assert_close(p, ref_p, rtol=1e-6, atol=1e-9)
+    assert torch.equal(params[0], params[1])
