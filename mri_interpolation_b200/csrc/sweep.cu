@@ -80,11 +80,11 @@ __device__ __forceinline__ void gather_feat(const float* __restrict__ row, float
 
 // One thread per voxel: coords -> L levels x 2^D gathers -> first decoder layer accumulated level by
 // level in registers (weights broadcast from shared memory) -> activation -> H->1 output layer.
-template <int D, int F, int H>
+template <int D, int F, int H, int ACT1>
 __global__ void __launch_bounds__(128) hashmlp_sweep_kernel(const float* __restrict__ axes, const GridDesc gd, int64_t first,
                                                             int64_t count, const float* __restrict__ tables,
                                                             const __grid_constant__ LevelTable T, int n_levels,
-                                                            const float* __restrict__ decoder, int act, int last_act,
+                                                            const float* __restrict__ decoder, int last_act,
                                                             float* __restrict__ out) {
   constexpr int C = 1 << D;
   extern __shared__ __align__(16) float smem[];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(128) hashmlp_sweep_kernel(const float* __restr
     }
     float y = b1[0];
 #pragma unroll
-    for (int j = 0; j < H; ++j) y = fmaf(activate_rt(act, h[j], 1.0f), w1[j], y);
+    for (int j = 0; j < H; ++j) y = fmaf(activate<ACT1>(h[j], 1.0f), w1[j], y);  // compile-time activation: 3x less code
     out[i] = activate_rt(last_act, y, 1.0f);
   }
 }
@@ -177,21 +177,29 @@ int make_grid_desc(const int32_t* host_shape, int dim, GridDesc* gd, int64_t* to
   return MRI_OK;
 }
 
-template <int D, int F, int H>
-int launch_sweep(const float* axes, const GridDesc& gd, int64_t first, int64_t count, const float* tables,
-                 const LevelTable& T, int n_levels, const float* decoder, int act, int last_act, float* out,
-                 cudaStream_t s) {
+template <int D, int F, int H, int ACT1>
+int launch_sweep_act(const float* axes, const GridDesc& gd, int64_t first, int64_t count, const float* tables,
+                     const LevelTable& T, int n_levels, const float* decoder, int last_act, float* out, cudaStream_t s) {
   const size_t smem = (static_cast<size_t>(n_levels) * F * H + 2 * H + 4) * sizeof(float);
   if (smem > 48 * 1024)
-    MRI_CUDA_OK(cudaFuncSetAttribute(hashmlp_sweep_kernel<D, F, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MRI_CUDA_OK(cudaFuncSetAttribute(hashmlp_sweep_kernel<D, F, H, ACT1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(smem)));
   int64_t blocks = (count + 127) / 128;
   const int64_t cap = 16LL * sm_count();
   if (blocks > cap) blocks = cap;
-  hashmlp_sweep_kernel<D, F, H><<<static_cast<int>(blocks), 128, smem, s>>>(axes, gd, first, count, tables, T, n_levels,
-                                                                            decoder, act, last_act, out);
+  hashmlp_sweep_kernel<D, F, H, ACT1><<<static_cast<int>(blocks), 128, smem, s>>>(axes, gd, first, count, tables, T, n_levels,
+                                                                                  decoder, last_act, out);
   MRI_LAUNCH_OK("hashmlp_sweep_kernel");
   return MRI_OK;
+}
+
+template <int D, int F, int H>
+int launch_sweep(const float* axes, const GridDesc& gd, int64_t first, int64_t count, const float* tables,
+                 const LevelTable& T, int n_levels, const float* decoder, int act, int last_act, float* out,
+                 cudaStream_t s) {
+  if (act == MRI_ACT_GELU) return launch_sweep_act<D, F, H, MRI_ACT_GELU>(axes, gd, first, count, tables, T, n_levels, decoder, last_act, out, s);
+  if (act == MRI_ACT_RELU) return launch_sweep_act<D, F, H, MRI_ACT_RELU>(axes, gd, first, count, tables, T, n_levels, decoder, last_act, out, s);
+  return fail(MRI_ERR_UNSUPPORTED, "hashmlp_sweep: fused kernel covers GELU / ReLU hidden activations (got %d)", act);
 }
 
 template <int D, int F>

@@ -47,6 +47,8 @@ def _fused_plan(model) -> Optional[dict]:
     l0, l1 = model.decoder[0][0], model.decoder[1][0]
     if l1.out_features != 1 or l0.out_features not in (16, 32, 64, 128) or l0.bias is None or l1.bias is None:
         return None
+    if acts[0] not in (_lib.ACT_GELU, _lib.ACT_RELU):
+        return None  # the fused kernel is compiled for GELU / ReLU hidden activations
     return dict(acts=acts, l0=l0, l1=l1)
 
 
