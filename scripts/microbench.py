@@ -178,3 +178,19 @@ if "levels" in which:
     res["hashgrid_bwd_per_level_us"] = per
     json.dump({**prev, **res}, open(out, "w"), indent=1)
     print(json.dumps(per, indent=0))
+
+if "sirenlayer" in which:
+    # one hidden layer of the 8x1024 SIREN at n = 2^17: forward (sine epilogue), dgrad, wgrad - the ncu target
+    n, h = 1 << 17, 1024
+    a = torch.rand(n, h, device=dev) * 2 - 1
+    w = (torch.rand(h, h, device=dev) * 2 - 1) * (6.0 / h) ** 0.5 / 30
+    b = torch.zeros(h, device=dev)
+    a_hi, a_lo = tc.split(a)
+    w_hi, w_lo = tc.split(w)
+    gw = torch.zeros(h, h, device=dev)
+    for _ in range(4):
+        oh, ol, _, aux = tc.layer(a_hi, a_lo, w_hi, w_lo, b, ACT_SINE, 30.0, passes=3, want_planes=True, want_aux=True)
+        tc.wgrad(a_hi, a_lo, oh, ol, gw, None, passes=3)
+        tc.dgrad(a_hi, a_lo, w_hi, w_lo, passes=3, mul=aux, want_planes=True)
+    torch.cuda.synchronize()
+    print("sirenlayer done")
