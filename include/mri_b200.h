@@ -117,6 +117,17 @@ int mri_decoder2_backward(const float* enc, int64_t n, int k0, int h, const floa
                           float* grad_enc, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
                           void* stream);
 
+/* Decoder backward FUSED with the hash-grid scatter (autograd of models.py:741-744 in one kernel): as
+ * mri_decoder2_backward, but dEnc never goes to memory - it is scattered straight into grad_tables
+ * (grad_tables[h_c] += w_c * dEnc, same arena layout as mri_hashgrid_backward).  Covers the headline geometry
+ * (F = 2, L = 16, hidden 64, dim 3/4, GELU/ReLU): query with mri_hashdecoder_supported. */
+int mri_hashdecoder_supported(int dim, int n_levels, int n_features, int h, int act1);
+int mri_hashdecoder_backward(const float* x, int64_t n, int dim, const float* enc, int k0, int h, const float* w1,
+                             const float* b1, const float* w2, const float* pre2, const float* grad_y, int act1,
+                             int act2, float* grad_tables, const mri_level_t* host_levels, int n_levels,
+                             int n_features, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
+                             void* stream);
+
 /* ---- wide SIREN layers on tcgen05 tensor cores ------------------------------------------------ */
 
 /* 1 if a layer with `k` inputs and `m` outputs is taken by the tcgen05 path (multiples of 64). */

@@ -225,6 +225,70 @@ class Decoder2Fn(torch.autograd.Function):
         return (genc.reshape(ctx.enc_shape), ret[0], ret[1], ret[2], ret[3], None, None)
 
 
+class HashDecoderFn(torch.autograd.Function):
+    """Hash-grid encoder + 2-layer decoder as ONE autograd node: forward = gather kernel + tensor-core decoder,
+    backward = ONE kernel (decoder backward with the table scatter fused in: dEnc never touches memory)."""
+
+    @staticmethod
+    def forward(ctx, x, grid, w1, b1, w2, b2, act1: int, act2: int, *tables):
+        n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
+        x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
+        n = x2.shape[0]
+        for t in tables:
+            _lib.require_cuda_f32(t, "hash table")
+        grid._fwd_layout.refresh(tables, grid._resolutions, grid._rows)
+        enc = torch.empty((n, n_levels * nf), device=x.device, dtype=torch.float32)
+        _lib.call("mri_hashgrid_forward", x2.data_ptr(), n, dim, grid._fwd_layout.base, grid._fwd_layout.levels, n_levels, nf,
+                  enc.data_ptr(), _lib.stream())
+        h, k0 = w1.shape
+        y = torch.empty((n, 1), device=x.device, dtype=torch.float32)
+        train = w1.requires_grad or any(t.requires_grad for t in tables)
+        pre2 = torch.empty((n,), device=x.device, dtype=torch.float32) if train else None
+        _lib.call("mri_decoder2_forward", enc.data_ptr(), n, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                  act1, act2, y.data_ptr(), _lib.ptr(pre2), _lib.stream())
+        ctx.grid, ctx.acts = grid, (act1, act2)
+        ctx.params, ctx.tables = (w1, b1, w2, b2), tables
+        ctx.save_for_backward(x2, enc, pre2)
+        return y.reshape(*x.shape[:-1], 1)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        grid = ctx.grid
+        x2, enc, pre2 = ctx.saved_tensors
+        w1, b1, w2, b2 = ctx.params
+        tables = ctx.tables
+        n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
+        h, k0 = w1.shape
+        n = x2.shape[0]
+        gy = grad_y.reshape(n).contiguous()
+        pgrads, pret = [], []
+        for p in (w1, b1, w2, b2):
+            d = _direct_grad(p)
+            pgrads.append(d if d is not None else torch.zeros_like(p))
+            pret.append(None if d is not None else pgrads[-1])
+        direct = [_direct_grad(t) for t in tables]
+        if all(d is not None for d in direct):
+            targets, tret = direct, (None,) * len(tables)
+        else:
+            sizes = [(t.numel() + 3) // 4 * 4 for t in tables]
+            flat = torch.zeros(sum(sizes), device=gy.device, dtype=torch.float32)
+            targets, off = [], 0
+            for t, s in zip(tables, sizes):
+                targets.append(flat[off:off + t.numel()].view_as(t))
+                off += s
+            tret = tuple(targets)
+        grid._bwd_layout.refresh(targets, grid._resolutions, grid._rows)
+        _lib.call("mri_hashdecoder_backward", x2.data_ptr(), n, dim, enc.data_ptr(), k0, h, w1.data_ptr(), b1.data_ptr(),
+                  w2.data_ptr(), pre2.data_ptr(), gy.data_ptr(), ctx.acts[0], ctx.acts[1], grid._bwd_layout.base,
+                  grid._bwd_layout.levels, n_levels, nf, pgrads[0].data_ptr(), pgrads[1].data_ptr(), pgrads[2].data_ptr(),
+                  pgrads[3].data_ptr(), _lib.stream())
+        return (None, None, pret[0], pret[1], pret[2], pret[3], None, None) + tret
+
+
+def hashdecoder_supported(dim: int, n_levels: int, n_features: int, h: int, act1: int) -> bool:
+    return bool(_lib.lib().mri_hashdecoder_supported(int(dim), int(n_levels), int(n_features), int(h), int(act1)))
+
+
 def decoder2_supported(k0: int, h: int, act1: int) -> bool:
     return bool(_lib.lib().mri_decoder2_supported(int(k0), int(h), int(act1)))
 

@@ -17,6 +17,7 @@ the C ABI (csrc/*.cu); inputs/parameters must be CUDA fp32 - there is no CPU fal
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Tuple
 
 import torch
@@ -298,6 +299,7 @@ class HashMLP(BaseMLP):
         self.batch_norm = batch_norm
         self.latents = []  # encoder outputs kept by predict_step for visualisation (:689,749)
         self.keep_latents = True
+        self.fuse_backward = os.environ.get("MRI_FUSED_BACKWARD", "1") == "1"
 
         if isinstance(self.base_resolution, int):
             self.encoder = encoding.MultiResHashGrid(
@@ -368,6 +370,13 @@ class HashMLP(BaseMLP):
         return z
 
     def forward(self, x):
+        plan = self._fused_decoder_plan() if x.is_cuda else None
+        enc = self.encoder
+        if (plan is not None and self.fuse_backward and getattr(enc, "_resolutions", None) is not None
+                and Fn.hashdecoder_supported(enc.dim, enc.n_levels, enc.n_features_per_level, plan[0].out_features, plan[2])):
+            # encoder + decoder as one autograd node: the backward is ONE kernel (decoder backward + table scatter)
+            l1, l2, a1, a2 = plan
+            return Fn.HashDecoderFn.apply(x, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2, *enc.tables())
         return self.decode(self.encoder(x))
 
     def predict_step(self, batch, batch_idx):

@@ -263,3 +263,41 @@ def test_sharded_adam_kernel_emulated_two_ranks_on_one_gpu():
     for p in params:
         torch.testing.assert_close(p, ref_p, rtol=1e-6, atol=1e-9)
     assert torch.equal(params[0], params[1])
+
+
+def test_fused_hashdecoder_backward_matches_unfused_and_oracle():
+    """G4-shaped model (L=16, F=2, hidden 64): encoder+decoder backward in one kernel vs the two-kernel path vs the oracle."""
+    import copy
+    from mri_interpolation_b200 import models
+    from oracle import networks
+    kw = dict(dim_in=4, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=200,
+              dim_hidden=64, dim_out=1, n_layers=2)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False)
+    gen = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
+    params = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items() if not k.startswith("layers.")}
+    levels = networks.hashgrid.geometry(4, 16, 12, 16, 200)
+    for n in (1, 33, 5000):
+        x, y = torch.rand(n, 4, generator=gen), torch.rand(n, 1, generator=gen)
+        for p in params.values():
+            p.grad = None
+        F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, False)).backward()
+        fused, plain = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
+        plain.fuse_backward = False
+        lf = fused.training_step((x.to(DEV), y.to(DEV)), 0)
+        lf.backward()
+        lp = plain.training_step((x.to(DEV), y.to(DEV)), 0)
+        lp.backward()
+        assert abs(float(lf) - float(lp)) < 1e-6
+        for (name, pf), (_, pp) in zip(fused.named_parameters(), plain.named_parameters()):
+            if name.startswith("layers."):
+                continue
+            ref = params[name].grad
+            scale = float(ref.abs().max()) + 1e-12
+            assert float((pf.grad.cpu() - ref).abs().max()) < 2e-3 * scale, (n, name)
+            assert float((pf.grad - pp.grad).abs().max()) < 2e-3 * scale, (n, name)
+            if n >= 33:
+                assert rel_err(pf.grad, ref) < 1e-3, (n, name)
