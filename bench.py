@@ -463,6 +463,14 @@ def main():
                 fwd_ms = timed(lambda: enc(x))
             enc_out = enc(x)
             bwd_ms = timed(lambda: torch.autograd.backward(enc_out, go, retain_graph=True))
+            # the whole-model backward (ONE kernel when the decoder backward is fused with the scatter)
+            fused_ms = None
+            if getattr(model, "fuse_backward", False):
+                pred = model(x)
+                gy = torch.randn_like(pred) * 1e-3
+                if pred.grad_fn is not None and type(pred.grad_fn).__name__.startswith("HashDecoderFn"):
+                    fused_ms = timed(lambda: torch.autograd.backward(pred, gy, retain_graph=True))
+                del pred
             opt.arena.grad.zero_()
             # the single-GPU Adam kernel on scratch arenas of the model's size (the model itself is not stepped here)
             scratch = [torch.zeros(opt.arena.numel, device=dev) for _ in range(4)]
@@ -478,12 +486,21 @@ def main():
                 "adam_step": {"ms": adam_ms, "GBps_algorithmic": adam_bytes / adam_ms / 1e6, "frac": adam_bytes / adam_ms / 1e6 / hbm_peak},
             }
             top = "hashgrid_bwd" if bwd_ms >= fwd_ms else "hashgrid_fwd"
+            traffic = 320.7e6 if top == "hashgrid_bwd" else 235.2e6
+            if fused_ms is not None:
+                # fused decoder-backward + scatter: coords + enc + dy read, L*2^D*F*4 B reduced into the tables
+                fused_bytes = (HASH_BYTES_PER_COORD + 4) * n
+                kern["hashdecoder_bwd"] = {"ms": fused_ms, "GBps_algorithmic": fused_bytes / fused_ms / 1e6,
+                                           "frac": fused_bytes / fused_ms / 1e6 / hbm_peak}
+                if fused_ms >= max(fwd_ms, bwd_ms):
+                    top, hash_bytes, traffic = "hashdecoder_bwd", fused_bytes, None
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[top]["frac"], "traffic": 320.7e6 if top == "hashgrid_bwd" else 235.2e6,
+                    "frac": kern[top]["frac"], "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": hash_bytes,
-                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x 2^19 coords; traffic = ncu "
-                            "dram read+write per launch (profiles/r01_ncu_full_hash_adam.csv): the 61 MB of tables stay in "
-                            "the 126 MB L2, the kernel is bound by the L1/L2 sector rate (lts 76%, l1tex 74-88% of peak)"}
+                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x 2^19 coords (+4 B/coord dy for "
+                            "the fused decoder-backward+scatter kernel, which also does 8.4 kMAC/coord of decoder math); traffic "
+                            "= ncu dram read+write per launch (profiles/r01_ncu_full_hash_adam.csv): the 61 MB of tables stay "
+                            "in the 126 MB L2, the kernels are bound by the L1/L2 sector and L2 atomic rates, not HBM"}
         else:
             from mri_interpolation_b200 import tc
             from mri_interpolation_b200._lib import ACT_SINE

@@ -128,6 +128,14 @@ int mri_hashdecoder_backward(const float* x, int64_t n, int dim, const float* en
                              int n_features, float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2,
                              void* stream);
 
+/* Encoder + decoder forward in ONE kernel for the same geometry (models.py:741-744: decoder(encoder(x))): the
+ * gather produces the tensor-core fragments of the first decoder layer in registers.  enc (n, 32) is written when
+ * non-NULL (bit-identical to mri_hashgrid_forward; the backward needs it), pre2 (n) likewise; y (n) always. */
+int mri_hashdecoder_forward(const float* x, int64_t n, int dim, const float* tables, const mri_level_t* host_levels,
+                            int n_levels, int n_features, int k0, int h, const float* w1, const float* b1,
+                            const float* w2, const float* b2, int act1, int act2, float* enc, float* y, float* pre2,
+                            void* stream);
+
 /* ---- wide SIREN layers on tcgen05 tensor cores ------------------------------------------------ */
 
 /* 1 if a layer with `k` inputs and `m` outputs is taken by the tcgen05 path (multiples of 64). */

@@ -13,11 +13,11 @@
 
 #include "common.cuh"
 #include "hash_device.cuh"
+#include "mma_device.cuh"
 
 namespace mri {
 namespace {
 
-constexpr int DEC_THREADS = 128;
 constexpr int DP_PAD = 4;  // dPre1 rows are H + 4 floats apart: conflict-free float4 stores, still 16-byte aligned
 
 template <int ACT>
@@ -236,75 +236,6 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decoder2_bwd_kernel(const floa
 // straight from global memory (A: float2 loads in the fragment's own (row g, cols 2t) pattern) and from a padded
 // bf16 copy of W1 in shared memory (B); bias, GELU, the H -> 1 output layer and its quad reduction happen on the
 // accumulator fragments in registers.  ~3x fewer issued instructions than the CUDA-core kernel above.
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
-  const __nv_bfloat162 h = __halves2bfloat162(hx, hy);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __bfloat162float(hx), y - __bfloat162float(hy));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-constexpr int MMA_PAD = 8;  // bf16 elements of row padding: conflict-free 32-bit fragment loads
-
-// W (rows x cols, fp32, row-major in global) -> two padded bf16 planes in shared memory
-template <int ROWS, int COLS>
-__device__ __forceinline__ void stage_planes(const float* __restrict__ w, __nv_bfloat16* hi, __nv_bfloat16* lo, bool transpose) {
-  for (int e = threadIdx.x; e < ROWS * COLS; e += DEC_THREADS) {
-    const int r = e / COLS, c = e - r * COLS;
-    const float v = __ldg(w + e);
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const int dst = transpose ? (c * (ROWS + MMA_PAD) + r) : (r * (COLS + MMA_PAD) + c);
-    hi[dst] = h;
-    lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
-  }
-}
-
-// A fragments (hi/lo) of one 16-coordinate m-tile: rows (g, g+8) of `enc`, all K0 columns
-template <int K0>
-__device__ __forceinline__ void load_a_frags(const float* __restrict__ enc, int64_t row0, int64_t n, int g, int t,
-                                             uint32_t (&a_hi)[K0 / 16][4], uint32_t (&a_lo)[K0 / 16][4]) {
-  const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
-#pragma unroll
-  for (int kt = 0; kt < K0 / 16; ++kt) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int col = 16 * kt + 8 * half + 2 * t;
-      float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-      if (r_lo < n) v0 = __ldg(reinterpret_cast<const float2*>(enc + r_lo * K0 + col));
-      if (r_hi < n) v1 = __ldg(reinterpret_cast<const float2*>(enc + r_hi * K0 + col));
-      split_pair(v0.x, v0.y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
-      split_pair(v1.x, v1.y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
-    }
-  }
-}
-
-// acc[nt] (16 x 8 tiles over the H hidden units) = bias + A . W1^T with the 3-pass split product
-template <int K0, int H>
-__device__ __forceinline__ void hidden_mma(const uint32_t (&a_hi)[K0 / 16][4], const uint32_t (&a_lo)[K0 / 16][4],
-                                           const __nv_bfloat16* __restrict__ w_hi, const __nv_bfloat16* __restrict__ w_lo,
-                                           const float* __restrict__ b1s, int g, int t, float (&acc)[H / 8][4]) {
-  constexpr int WS = K0 + MMA_PAD;
-#pragma unroll
-  for (int nt = 0; nt < H / 8; ++nt) {
-    const float bl = b1s[8 * nt + 2 * t], bh = b1s[8 * nt + 2 * t + 1];
-    acc[nt][0] = bl; acc[nt][1] = bh; acc[nt][2] = bl; acc[nt][3] = bh;
-#pragma unroll
-    for (int kt = 0; kt < K0 / 16; ++kt) {
-      const int off = (8 * nt + g) * WS + 16 * kt + 2 * t;
-      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(w_hi + off), bh1 = *reinterpret_cast<const uint32_t*>(w_hi + off + 8);
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(w_lo + off), bl1 = *reinterpret_cast<const uint32_t*>(w_lo + off + 8);
-      mma_bf16_16816(acc[nt], a_lo[kt], bh0, bh1);
-      mma_bf16_16816(acc[nt], a_hi[kt], bl0, bl1);
-      mma_bf16_16816(acc[nt], a_hi[kt], bh0, bh1);
-    }
-  }
-}
-
 template <int K0, int H, int ACT1>
 __global__ void __launch_bounds__(DEC_THREADS, 3) decoder2_mma_fwd_kernel(const float* __restrict__ enc, int64_t n,
                                                                            const float* __restrict__ w1, const float* __restrict__ b1,
@@ -603,6 +534,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
     b1s[e] = __ldg(b1 + e);
     w2s[e] = __ldg(w2 + e);
   }
+  // the lanes of one instruction work on two different levels: a lane-indexed read of the __grid_constant__ table is a
+  // replayed LDC on the long scoreboard (17 % of the stall samples in ncu) - shared memory serves it in one pass
+  __shared__ LevelDev lvs[K0 / 2];
+  if (threadIdx.x < K0 / 2) lvs[threadIdx.x] = T.lv[threadIdx.x];
   __syncthreads();
 
   float wacc[H / 16][K0 / 8][4];
@@ -617,20 +552,55 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
   for (int nt = 0; nt < H / 8; ++nt) { pb1[nt][0] = pb1[nt][1] = 0.0f; pw2[nt][0] = pw2[nt][1] = 0.0f; }
   float pb2 = 0.0f;
 
+  // inputs of one 16-row m-tile as they come out of global memory; the next tile's are requested before the current
+  // tile is processed (2 warps per scheduler cannot hide a DRAM round trip per tile on their own)
+  struct TileIn {
+    float2 e[K0 / 16][2][2];  // [k-tile][8-column half][row g / g+8]
+    float gy[2], p2[2];
+    float xv[2][D];
+  };
+  auto fetch = [&](int64_t row0, TileIn& ti) {
+    const int64_t r[2] = {row0 + g, row0 + g + 8};
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const bool live = r[rr] < n;
+      load_coord<D>(x, live ? r[rr] : 0, ti.xv[rr]);
+      ti.gy[rr] = live ? __ldg(gy + r[rr]) : 0.0f;
+      ti.p2[rr] = live ? __ldg(pre2 + r[rr]) : 0.0f;
+#pragma unroll
+      for (int kt = 0; kt < K0 / 16; ++kt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          ti.e[kt][half][rr] = live ? __ldg(reinterpret_cast<const float2*>(enc + r[rr] * K0 + 16 * kt + 8 * half + 2 * t))
+                                    : make_float2(0.0f, 0.0f);
+    }
+  };
+
   const int64_t chunks = (n + 31) / 32;
-  for (int64_t chunk = static_cast<int64_t>(blockIdx.x) * NWARP + warp; chunk < chunks;
-       chunk += static_cast<int64_t>(gridDim.x) * NWARP) {
+  const int64_t chunk_stride = static_cast<int64_t>(gridDim.x) * NWARP;
+  int64_t chunk = static_cast<int64_t>(blockIdx.x) * NWARP + warp;
+  TileIn nxt;
+  fetch(chunk * 32, nxt);
+  for (; chunk < chunks; chunk += chunk_stride) {
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
       const int64_t row0 = chunk * 32 + 16 * mt;
       const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
+      const TileIn cur = nxt;
+      fetch(mt == 0 ? row0 + 16 : (chunk + chunk_stride) * 32, nxt);
       float xv_lo[D], xv_hi[D];
-      load_coord<D>(x, r_lo < n ? r_lo : 0, xv_lo);
-      load_coord<D>(x, r_hi < n ? r_hi : 0, xv_hi);
+#pragma unroll
+      for (int d = 0; d < D; ++d) { xv_lo[d] = cur.xv[0][d]; xv_hi[d] = cur.xv[1][d]; }
       float acc[H / 8][4];
       {
         uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
-        load_a_frags<K0>(enc, row0, n, g, t, a_hi, a_lo);
+#pragma unroll
+        for (int kt = 0; kt < K0 / 16; ++kt)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
+            split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+          }
 #pragma unroll
         for (int kt = 0; kt < K0 / 16; ++kt)
 #pragma unroll
@@ -644,8 +614,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
         hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
       }
       float dp2_lo = 0.0f, dp2_hi = 0.0f;
-      if (r_lo < n) dp2_lo = __ldg(gy + r_lo) * activate_grad_rt(act2, __ldg(pre2 + r_lo), 1.0f);
-      if (r_hi < n) dp2_hi = __ldg(gy + r_hi) * activate_grad_rt(act2, __ldg(pre2 + r_hi), 1.0f);
+      if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
+      if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
       if (t == 0) pb2 += dp2_lo + dp2_hi;
       uint32_t da_hi[H / 16][4], da_lo[H / 16][4];
 #pragma unroll
@@ -694,7 +664,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
         for (int which = 0; which < 2; ++which) {  // 0: the pair's even level, 1: its odd level
           const int level = 4 * nt2 + (t & ~1) + which;
           const bool mine = (which == b0);
-          const LevelDev& lv = T.lv[level];
+          const LevelDev lv = lvs[level];
           float* tbl = grad_tables + lv.offset;
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {  // rows g and g + 8 of the m-tile

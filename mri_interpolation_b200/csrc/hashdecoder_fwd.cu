@@ -1,0 +1,205 @@
+// Hash-grid encoder fused with the 2-layer decoder, forward direction (HashMLP.forward: models.py:712-739 on top of
+// encoding.py:190-191), for the headline geometry F = 2, L = 16 (K0 = 32), H = 64, D = 3 / 4.
+//
+// One warp owns a 16-coordinate m-tile of the mma.sync.m16n8k16 product enc(16 x 32) . W1^T(32 x 64).  The A fragment
+// of lane (g, t) holds rows g / g+8 and, per 8-column half of a k-tile, columns 2t, 2t+1 - i.e. exactly the two
+// features of ONE level (4q + t for the q-th half).  So the gather is laid out to produce fragments directly:
+// lanes t and t^1 form the pair of the pair-lane mapping (hash_device.cuh), each walks its axis-0 half of the corners
+// of the pair's two levels for both rows, one shuffle completes the level sums, and the interpolated features are
+// split into bf16 hi/lo planes in registers.  The (n, 32) encoding is written only when the backward needs it
+// (training); inference (the dense sweep) writes 4 bytes per voxel.  The gather kernel alone is bound by the L1/L2
+// sector rate with the issue slots 80 % idle - the tensor-core and GELU work of the decoder hides in those slots.
+//
+// Summation order of a level (lower axis-0 half + upper half) is the stand-alone kernel's, so `enc` is bit-identical
+// to mri_hashgrid_forward; the decoder arithmetic is decoder2_mma_fwd_kernel's (3-pass split product, fp32 parity).
+#include "common.cuh"
+#include "grid_device.cuh"
+#include "hash_device.cuh"
+#include "mma_device.cuh"
+
+namespace mri {
+namespace {
+
+// coordinates of rows (row0 + g, row0 + g + 8) of a tile, from a (n, D) batch ...
+template <int D>
+struct BatchCoords {
+  const float* x;
+  __device__ __forceinline__ void load_pair(int64_t row0, int64_t n, int lane, float (&lo)[D], float (&hi)[D]) const {
+    const int64_t r_lo = row0 + (lane >> 2), r_hi = r_lo + 8;
+    load_coord<D>(x, r_lo < n ? r_lo : 0, lo);
+    load_coord<D>(x, r_hi < n ? r_hi : 0, hi);
+  }
+};
+// ... or synthesised from the flat voxel index of a dense grid: lanes 0-15 each decompose one index, the quads pick
+// their two rows up with shuffles (no 4x redundant integer divisions)
+template <int D>
+struct SweepCoords {
+  const float* axes;
+  GridDesc gd;
+  int64_t first;
+  __device__ __forceinline__ void load_pair(int64_t row0, int64_t n, int lane, float (&lo)[D], float (&hi)[D]) const {
+    const int64_t r = row0 + (lane & 15);
+    float v[D];
+    voxel_coord<D>(axes, gd, first + (r < n ? r : 0), v);
+    const int g = lane >> 2;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      lo[d] = __shfl_sync(0xffffffffu, v[d], g);
+      hi[d] = __shfl_sync(0xffffffffu, v[d], g + 8);
+    }
+  }
+};
+
+template <int D, int K0, int H, int ACT1, class Coords>
+__global__ void __launch_bounds__(DEC_THREADS, 3) hashdecoder_mma_fwd_kernel(const Coords src, int64_t n,
+                                                                             const float* __restrict__ tables,
+                                                                             const __grid_constant__ LevelTable T,
+                                                                             const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                             int act2, float* __restrict__ enc_out,
+                                                                             float* __restrict__ y, float* __restrict__ pre2_out) {
+  static_assert(K0 == 32, "two k-tiles: 16 levels of 2 features");
+  constexpr int WS = K0 + MMA_PAD;
+  __shared__ __align__(16) __nv_bfloat16 w_hi[H * WS];
+  __shared__ __align__(16) __nv_bfloat16 w_lo[H * WS];
+  __shared__ float b1s[H];
+  __shared__ float w2s[H];
+  __shared__ LevelDev lvs[K0 / 2];  // lanes of one instruction work on two different levels: shared memory, not c[] replays
+  stage_planes<H, K0>(w1, w_hi, w_lo, false);
+  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+    b1s[e] = __ldg(b1 + e);
+    w2s[e] = __ldg(w2 + e);
+  }
+  if (threadIdx.x < K0 / 2) lvs[threadIdx.x] = T.lv[threadIdx.x];
+  const float b2v = __ldg(b2);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int b0 = t & 1;  // axis-0 half of the pair-lane mapping
+  const int64_t tiles = (n + 15) / 16;
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (DEC_THREADS / 32) + warp; tile < tiles;
+       tile += static_cast<int64_t>(gridDim.x) * (DEC_THREADS / 32)) {
+    const int64_t row0 = tile * 16;
+    const int64_t rows[2] = {row0 + g, row0 + g + 8};
+    float xv[2][D];
+    src.load_pair(row0, n, lane, xv[0], xv[1]);
+    uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
+#pragma unroll
+    for (int q = 0; q < K0 / 8; ++q) {  // q-th 8-column half: levels 4q .. 4q+3, this lane ends up with level 4q + t
+      Feat<2> part[2][2];               // [level of the pair: even / odd][row g / g+8], this lane's axis-0 half
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const LevelDev lv = lvs[4 * q + (t & 2) + which];
+        const float* __restrict__ tbl = tables + lv.offset;
+        // one branch per level (a few coarse levels have non-power-of-two row counts), both rows inside it: the 16
+        // gathers of a level are straight-line code and go out back-to-back
+        if (lv.is_pow2) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) part[which][rr] = encode_half_level<D, 2, true>(make_cell<D>(xv[rr], lv), b0, lv, tbl);
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) part[which][rr] = encode_half_level<D, 2, false>(make_cell<D>(xv[rr], lv), b0, lv, tbl);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        float full[2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+          const float mine = b0 ? part[1][rr].v[f] : part[0][rr].v[f];
+          const float send = b0 ? part[0][rr].v[f] : part[1][rr].v[f];
+          full[f] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        split_pair(full[0], full[1], a_hi[q >> 1][2 * (q & 1) + rr], a_lo[q >> 1][2 * (q & 1) + rr]);
+        if (enc_out != nullptr && rows[rr] < n)
+          *reinterpret_cast<float2*>(enc_out + rows[rr] * K0 + 2 * (4 * q + t)) = make_float2(full[0], full[1]);
+      }
+    }
+    float acc[H / 8][4];
+    hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
+    float s_lo = 0.0f, s_hi = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < H / 8; ++nt) {
+      const float wl = w2s[8 * nt + 2 * t], wh = w2s[8 * nt + 2 * t + 1];
+      s_lo = fmaf(activate<ACT1>(acc[nt][0], 1.0f), wl, s_lo);
+      s_lo = fmaf(activate<ACT1>(acc[nt][1], 1.0f), wh, s_lo);
+      s_hi = fmaf(activate<ACT1>(acc[nt][2], 1.0f), wl, s_hi);
+      s_hi = fmaf(activate<ACT1>(acc[nt][3], 1.0f), wh, s_hi);
+    }
+    s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+    s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+    if (t == 0) {
+      if (rows[0] < n) { const float p = s_lo + b2v; y[rows[0]] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[rows[0]] = p; }
+      if (rows[1] < n) { const float p = s_hi + b2v; y[rows[1]] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[rows[1]] = p; }
+    }
+  }
+}
+
+template <int D, int ACT1, class Coords>
+int launch_fused_fwd(const Coords& src, int64_t n, const float* tables, const LevelTable& T, const float* w1, const float* b1,
+                     const float* w2, const float* b2, int act2, float* enc, float* y, float* pre2, cudaStream_t s) {
+  auto kernel = hashdecoder_mma_fwd_kernel<D, 32, 64, ACT1, Coords>;
+  static int resident = 0;  // persistent grid = exactly one wave (blocks walk the tiles with a grid stride): a cap that
+  if (resident == 0) {      // is not a multiple of the resident block count costs a whole extra pass of the tail blocks
+    int per_sm = 0;
+    MRI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DEC_THREADS, 0));
+    resident = (per_sm > 0 ? per_sm : 1) * sm_count();
+  }
+  int64_t blocks = ((n + 15) / 16 + 3) / 4;
+  if (blocks > resident) blocks = resident;
+  kernel<<<static_cast<int>(blocks), DEC_THREADS, 0, s>>>(src, n, tables, T, w1, b1, w2, b2, act2, enc, y, pre2);
+  MRI_LAUNCH_OK("hashdecoder_mma_fwd_kernel");
+  return MRI_OK;
+}
+
+bool geometry_ok(int dim, int n_levels, int n_features, int h, int act) {
+  return (dim == 3 || dim == 4) && n_levels == 16 && n_features == 2 && h == 64 && (act == MRI_ACT_GELU || act == MRI_ACT_RELU);
+}
+
+}  // namespace
+
+bool sweep_mma_supported(int dim, int n_levels, int n_features, int h, int act) {
+  return geometry_ok(dim, n_levels, n_features, h, act);
+}
+
+int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int64_t first, int64_t count, const float* tables,
+                     const LevelTable& T, const float* decoder, int act, int last_act, float* out, cudaStream_t s) {
+  constexpr int K0 = 32, H = 64;  // packed decoder: W1 (H x K0), b1 (H), w2 (H), b2 (1)
+  const float *w1 = decoder, *b1 = decoder + H * K0, *w2 = b1 + H, *b2 = w2 + H;
+#define CALL(DV, ACTV)                                                                                              \
+  launch_fused_fwd<DV, ACTV>(SweepCoords<DV>{axes, gd, first}, count, tables, T, w1, b1, w2, b2, last_act, nullptr, out, \
+                             nullptr, s)
+  if (dim == 3) return act == MRI_ACT_GELU ? CALL(3, MRI_ACT_GELU) : CALL(3, MRI_ACT_RELU);
+  return act == MRI_ACT_GELU ? CALL(4, MRI_ACT_GELU) : CALL(4, MRI_ACT_RELU);
+#undef CALL
+}
+
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_hashdecoder_forward(const float* x, int64_t n, int dim, const float* tables, const mri_level_t* host_levels,
+                                       int n_levels, int n_features, int k0, int h, const float* w1, const float* b1,
+                                       const float* w2, const float* b2, int act1, int act2, float* enc, float* y, float* pre2,
+                                       void* stream) {
+  if (n < 0) return fail(MRI_ERR_INVALID, "hashdecoder_forward: negative n");
+  if (n == 0) return MRI_OK;
+  if (!x || !tables || !host_levels || !w1 || !b1 || !w2 || !b2 || !y)
+    return fail(MRI_ERR_INVALID, "hashdecoder_forward: null pointer");
+  if (k0 != 2 * n_levels || !geometry_ok(dim, n_levels, n_features, h, act1))
+    return fail(MRI_ERR_UNSUPPORTED, "hashdecoder_forward: fused kernel covers F=2, L=16, H=64, dim 3/4, GELU/ReLU "
+                                     "(got F=%d L=%d H=%d dim=%d act=%d)", n_features, n_levels, h, dim, act1);
+  const uintptr_t need = dim == 4 ? 15 : 3;
+  if ((reinterpret_cast<uintptr_t>(x) & need) || (reinterpret_cast<uintptr_t>(tables) & 15) || (reinterpret_cast<uintptr_t>(enc) & 15))
+    return fail(MRI_ERR_INVALID, "hashdecoder_forward: misaligned pointer");
+  for (int l = 0; l < n_levels; ++l)
+    if (host_levels[l].offset % 2) return fail(MRI_ERR_INVALID, "hashdecoder_forward: level %d offset not aligned", l);
+  LevelTable T;
+  int st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(DV, ACTV) launch_fused_fwd<DV, ACTV>(BatchCoords<DV>{x}, n, tables, T, w1, b1, w2, b2, act2, enc, y, pre2, s)
+  if (dim == 3) return act1 == MRI_ACT_GELU ? CALL(3, MRI_ACT_GELU) : CALL(3, MRI_ACT_RELU);
+  return act1 == MRI_ACT_GELU ? CALL(4, MRI_ACT_GELU) : CALL(4, MRI_ACT_RELU);
+#undef CALL
+}

@@ -6,28 +6,13 @@
 // caller passes torch.linspace's output, so the floats are the reference's own), i.e. zero
 // coordinate traffic.  hashmlp_sweep_kernel additionally fuses the all-level hash encoding with
 // the 2-layer decoder: per voxel only the 4-byte result is written.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "grid_device.cuh"
 
 namespace mri {
 namespace {
-
-struct GridDesc {
-  int shape[MRI_MAX_DIM];
-  int axis_off[MRI_MAX_DIM];
-};
-
-template <int D>
-__device__ __forceinline__ void voxel_coord(const float* __restrict__ axes, const GridDesc& gd, int64_t idx, float (&v)[D]) {
-  uint64_t rem = static_cast<uint64_t>(idx);
-#pragma unroll
-  for (int d = D - 1; d >= 1; --d) {
-    const uint64_t q = rem / static_cast<uint32_t>(gd.shape[d]);
-    const uint32_t r = static_cast<uint32_t>(rem - q * static_cast<uint32_t>(gd.shape[d]));
-    v[d] = __ldg(axes + gd.axis_off[d] + r);
-    rem = q;
-  }
-  v[0] = __ldg(axes + gd.axis_off[0] + static_cast<uint32_t>(rem));
-}
 
 template <int D>
 __global__ void __launch_bounds__(256) grid_coords_kernel(const float* __restrict__ axes, const GridDesc gd, int64_t first,
@@ -159,24 +144,6 @@ __global__ void __launch_bounds__(128) hashmlp_sweep_kernel(const float* __restr
   }
 }
 
-int make_grid_desc(const int32_t* host_shape, int dim, GridDesc* gd, int64_t* total) {
-  int off = 0;
-  int64_t t = 1;
-  for (int d = 0; d < MRI_MAX_DIM; ++d) {
-    gd->shape[d] = 1;
-    gd->axis_off[d] = 0;
-  }
-  for (int d = 0; d < dim; ++d) {
-    if (host_shape[d] < 1) return fail(MRI_ERR_INVALID, "sweep: shape[%d] = %d", d, host_shape[d]);
-    gd->shape[d] = host_shape[d];
-    gd->axis_off[d] = off;
-    off += host_shape[d];
-    t *= host_shape[d];
-  }
-  *total = t;
-  return MRI_OK;
-}
-
 template <int D, int F, int H, int ACT1>
 int launch_sweep_act(const float* axes, const GridDesc& gd, int64_t first, int64_t count, const float* tables,
                      const LevelTable& T, int n_levels, const float* decoder, int last_act, float* out, cudaStream_t s) {
@@ -292,6 +259,9 @@ extern "C" int mri_hashmlp_sweep(const float* axes, const int32_t* host_shape, i
   if (st != MRI_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int H = host_dims[1];
+  static const bool use_cuda_cores = getenv("MRI_SWEEP_CUDA_CORES") != nullptr;  // debugging/profiling switch
+  if (!use_cuda_cores && sweep_mma_supported(dim, n_levels, n_features, H, act))
+    return launch_sweep_mma(axes, gd, dim, first, count, tables, T, decoder, act, last_act, out, s);
 #define CALL(D, F) dispatch_h<D, F>(H, axes, gd, first, count, tables, T, n_levels, decoder, act, last_act, out, s)
   switch (dim * 16 + n_features) {
     case 2 * 16 + 1: return CALL(2, 1);

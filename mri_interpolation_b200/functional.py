@@ -9,6 +9,7 @@ like any autograd gradient.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -225,9 +226,13 @@ class Decoder2Fn(torch.autograd.Function):
         return (genc.reshape(ctx.enc_shape), ret[0], ret[1], ret[2], ret[3], None, None)
 
 
+# MRI_FUSED_FORWARD=0 keeps the two-kernel forward (gather, then decoder) for profiling / A-B comparisons
+FUSED_FORWARD = os.environ.get("MRI_FUSED_FORWARD", "1") != "0"
+
+
 class HashDecoderFn(torch.autograd.Function):
-    """Hash-grid encoder + 2-layer decoder as ONE autograd node: forward = gather kernel + tensor-core decoder,
-    backward = ONE kernel (decoder backward with the table scatter fused in: dEnc never touches memory)."""
+    """Hash-grid encoder + 2-layer decoder as ONE autograd node: forward = ONE kernel (gather feeding the tensor-core
+    decoder in registers), backward = ONE kernel (decoder backward with the table scatter fused in: dEnc never touches memory)."""
 
     @staticmethod
     def forward(ctx, x, grid, w1, b1, w2, b2, act1: int, act2: int, *tables):
@@ -237,15 +242,23 @@ class HashDecoderFn(torch.autograd.Function):
         for t in tables:
             _lib.require_cuda_f32(t, "hash table")
         grid._fwd_layout.refresh(tables, grid._resolutions, grid._rows)
-        enc = torch.empty((n, n_levels * nf), device=x.device, dtype=torch.float32)
-        _lib.call("mri_hashgrid_forward", x2.data_ptr(), n, dim, grid._fwd_layout.base, grid._fwd_layout.levels, n_levels, nf,
-                  enc.data_ptr(), _lib.stream())
         h, k0 = w1.shape
         y = torch.empty((n, 1), device=x.device, dtype=torch.float32)
-        train = w1.requires_grad or any(t.requires_grad for t in tables)
+        train = any(ctx.needs_input_grad)  # all False under torch.no_grad(): nothing is kept for a backward
         pre2 = torch.empty((n,), device=x.device, dtype=torch.float32) if train else None
-        _lib.call("mri_decoder2_forward", enc.data_ptr(), n, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
-                  act1, act2, y.data_ptr(), _lib.ptr(pre2), _lib.stream())
+        if FUSED_FORWARD:
+            # ONE kernel: the gather feeds the decoder's tensor-core fragments in registers; the encoding is only
+            # written when the backward will need it
+            enc = torch.empty((n, n_levels * nf), device=x.device, dtype=torch.float32) if train else None
+            _lib.call("mri_hashdecoder_forward", x2.data_ptr(), n, dim, grid._fwd_layout.base, grid._fwd_layout.levels,
+                      n_levels, nf, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), act1, act2,
+                      _lib.ptr(enc), y.data_ptr(), _lib.ptr(pre2), _lib.stream())
+        else:
+            enc = torch.empty((n, n_levels * nf), device=x.device, dtype=torch.float32)
+            _lib.call("mri_hashgrid_forward", x2.data_ptr(), n, dim, grid._fwd_layout.base, grid._fwd_layout.levels, n_levels,
+                      nf, enc.data_ptr(), _lib.stream())
+            _lib.call("mri_decoder2_forward", enc.data_ptr(), n, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                      b2.data_ptr(), act1, act2, y.data_ptr(), _lib.ptr(pre2), _lib.stream())
         ctx.grid, ctx.acts = grid, (act1, act2)
         ctx.params, ctx.tables = (w1, b1, w2, b2), tables
         ctx.save_for_backward(x2, enc, pre2)

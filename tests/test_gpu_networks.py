@@ -301,3 +301,48 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle():
             assert float((pf.grad - pp.grad).abs().max()) < 2e-3 * scale, (n, name)
             if n >= 33:
                 assert rel_err(pf.grad, ref) < 1e-3, (n, name)
+
+
+@pytest.mark.parametrize("dim,act", [(4, "gelu"), (3, "relu")])
+def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(dim, act):
+    """Encoder+decoder forward in ONE kernel (mri_hashdecoder_forward): the encoding it writes is bit-identical to
+    mri_hashgrid_forward, the output equals the gather + decoder kernels and the oracle."""
+    from mri_interpolation_b200 import _lib, functional as Fn, models
+    from oracle import hashgrid, networks
+    kw = dict(dim_in=dim, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=300,
+              dim_hidden=64, dim_out=1, n_layers=2)
+    torch.manual_seed(7)
+    net = models.HashMLP(**kw, batch_norm=False, activation=torch.nn.ReLU if act == "relu" else torch.nn.GELU)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    levels = hashgrid.geometry(dim, 16, 12, 16, 300)
+    net = net.to(DEV)
+    enc_mod = net.encoder
+    l1, l2, a1, a2 = net._fused_decoder_plan()
+    for n in (1, 15, 16, 4099):
+        x = torch.rand(n, dim, generator=gen)
+        x[0, 0] = 1.0  # the reference does not clamp at the upper edge
+        xd = x.to(DEV)
+        with torch.no_grad():
+            enc_ref = enc_mod(xd)
+            y_two = Fn.Decoder2Fn.apply(enc_ref, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
+        tables = enc_mod.tables()
+        enc_mod._fwd_layout.refresh(tables, enc_mod._resolutions, enc_mod._rows)
+        enc = torch.full((n, 32), float("nan"), device=DEV)
+        y = torch.empty(n, 1, device=DEV)
+        pre2 = torch.empty(n, device=DEV)
+        _lib.call("mri_hashdecoder_forward", xd.data_ptr(), n, dim, enc_mod._fwd_layout.base, enc_mod._fwd_layout.levels, 16, 2,
+                  32, 64, l1.weight.data_ptr(), l1.bias.data_ptr(), l2.weight.data_ptr(), l2.bias.data_ptr(), a1, a2,
+                  enc.data_ptr(), y.data_ptr(), pre2.data_ptr(), _lib.stream())
+        assert torch.equal(enc, enc_ref), n
+        torch.testing.assert_close(y, y_two, rtol=1e-6, atol=1e-7)
+        ref = networks.hashmlp_forward(x, params, levels, 2, False, F.relu if act == "relu" else F.gelu)
+        assert float((y.cpu() - ref).abs().max()) < 1e-3 * (float(ref.abs().max()) + 1e-6), n
+        # module path: training forward keeps enc for the backward, no-grad forward writes only y
+        y_mod = net(xd)
+        with torch.no_grad():
+            y_eval = net(xd)
+        assert torch.equal(y_mod.detach(), y) and torch.equal(y_eval, y)
