@@ -7,15 +7,16 @@ voxels/s, with % of roofline and the reference's CPU path timed beside it).
 Workload (configs[1] of BASELINE.json, named in `config.workload`): hash-grid encoder G4
 (config/hash_config.json: L=16, F=2, T=2^19, base 16, x1.4 -> finest 2489; 15 279 648 table params)
 + 2-layer GELU decoder (64 hidden), fitted to the sample ankle volume (352x352x6x15, x,y,z,t coords),
-fp32, Adam lr 5e-3, 2^B coordinates per step PER GPU (weak scaling; N>1 adds one NCCL all-reduce of the
-flat gradient arena per step).  One step = sample voxel indices -> synthesise coords/gather intensities
--> hash encode -> decoder -> MSE -> backward (decoder, hash scatter) -> [all-reduce] -> fused Adam.
+fp32, Adam lr 5e-3, 2^B coordinates per step PER GPU (weak scaling; N>1 exchanges the flat gradient arena once
+per step inside the sharded Adam kernel).  One step = 5 kernels: sample voxel indices -> synthesise coords /
+gather intensities -> hash encode + decoder (one kernel) -> MSE -> decoder backward + hash scatter (one
+kernel) -> fused Adam [with the reduce-scatter / all-gather over NVLink at N>1].
 
 value : device-resident inputs, CUDA-event timing, max over ranks.
 e2e   : same step through the public LightningModule API with HOST (pinned) batches: H2D copy of the
         batch and D2H read of the loss inside the timed region.
-roofline : dominant kernel (hash-grid scatter backward) timed alone with CUDA events, L2 flushed between
-        launches; algorithmic bytes / duration against MEASURED_PEAKS.json's HBM copy bandwidth.
+roofline : dominant kernel (decoder backward fused with the hash-grid scatter) timed alone with CUDA events, L2
+        flushed between launches; algorithmic bytes / duration against MEASURED_PEAKS.json's HBM copy bandwidth.
 cpu_baseline : the oracle port of the reference's PyTorch path on this box's host cores (bounded sample).
 """
 from __future__ import annotations
@@ -38,6 +39,9 @@ SAMPLE = os.path.join(ROOT, "data", "sample_ankle_dyn_mri.nii.gz")
 SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (config 3)
 PRIMING_STEPS = 15  # allocator priming before the W warm-up steps (reported in config)
 HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of hashdecoder_mma_bwd_kernel at 2^19 coords (ncu --set full,
+# profiles/r01_ncu_full_fused_hashdecoder.csv): 137.9 MB read + 256.8 MB written
+FUSED_BWD_DRAM_BYTES = 394.6e6
 
 
 WORKLOADS = {
@@ -464,12 +468,13 @@ def main():
             enc_out = enc(x)
             bwd_ms = timed(lambda: torch.autograd.backward(enc_out, go, retain_graph=True))
             # the whole-model backward (ONE kernel when the decoder backward is fused with the scatter)
-            fused_ms = None
+            fused_ms = fused_fwd_ms = None
             if getattr(model, "fuse_backward", False):
                 pred = model(x)
                 gy = torch.randn_like(pred) * 1e-3
                 if pred.grad_fn is not None and type(pred.grad_fn).__name__.startswith("HashDecoderFn"):
                     fused_ms = timed(lambda: torch.autograd.backward(pred, gy, retain_graph=True))
+                    fused_fwd_ms = timed(lambda: model(x))  # training forward: gather + decoder, enc and pre2 written
                 del pred
             opt.arena.grad.zero_()
             # the single-GPU Adam kernel on scratch arenas of the model's size (the model itself is not stepped here)
@@ -492,8 +497,10 @@ def main():
                 fused_bytes = (HASH_BYTES_PER_COORD + 4) * n
                 kern["hashdecoder_bwd"] = {"ms": fused_ms, "GBps_algorithmic": fused_bytes / fused_ms / 1e6,
                                            "frac": fused_bytes / fused_ms / 1e6 / hbm_peak}
+                kern["hashdecoder_fwd"] = {"ms": fused_fwd_ms, "GBps_algorithmic": (fused_bytes + 4 * n) / fused_fwd_ms / 1e6,
+                                           "frac": (fused_bytes + 4 * n) / fused_fwd_ms / 1e6 / hbm_peak}
                 if fused_ms >= max(fwd_ms, bwd_ms):
-                    top, hash_bytes, traffic = "hashdecoder_bwd", fused_bytes, None
+                    top, hash_bytes, traffic = "hashdecoder_bwd", fused_bytes, FUSED_BWD_DRAM_BYTES
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kern[top]["frac"], "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": hash_bytes,

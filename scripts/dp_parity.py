@@ -17,7 +17,7 @@ from mri_interpolation_b200.optim import FusedAdam  # noqa: E402
 
 rank, local_rank, world = distributed.init_from_env("nccl")
 dev = torch.device("cuda", local_rank)
-kw = dict(dim_in=4, n_levels=8, n_features_per_level=2, log2_hashmap_size=15, base_resolution=8, finest_resolution=256,
+kw = dict(dim_in=4, n_levels=16, n_features_per_level=2, log2_hashmap_size=15, base_resolution=8, finest_resolution=256,
           dim_hidden=64, dim_out=1, n_layers=2, batch_norm=False, lr=5e-3)
 steps, n_global = 8, 1 << 16
 torch.manual_seed(1337)
