@@ -20,6 +20,10 @@ from . import _lib
 from ._lib import MriB200Error
 from .distributed import allreduce_sum_
 
+# multimem mode only: 1 = the owner of a slice clears it on every rank with a multicast store (one more arena of NVLink
+# ingress per rank and step), 0 = every rank clears its own gradient arena after the closing barrier
+_MULTICAST_CLEAR = os.environ.get("MRI_DP_MULTICAST_CLEAR", "0") == "1"
+
 _ALIGN = 4  # floats: every parameter starts 16-byte aligned inside the arena
 
 
@@ -239,17 +243,18 @@ class FusedAdam(torch.optim.Optimizer):
         if self.sharded and self._world() > 1:
             world = self._world()
             self.step_count += 1
+            remote_clear = bool(self._grad_mc) and _MULTICAST_CLEAR
             self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
             _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc, world,
                       dist.get_rank(self.process_group),
                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
                       float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                      (1.0 / world) if self.grad_average else 1.0, 1 if self._grad_mc else 0, _lib.stream())
+                      (1.0 / world) if self.grad_average else 1.0, 1 if remote_clear else 0, _lib.stream())
             # new parameters landed everywhere and every slice of my gradient arena has been read by its owner
             self.arena.data_hdl.barrier(channel=1)
-            if not self._grad_mc:
-                # P2P-pointer mode: clearing remotely would double the NVLink stores (measured 1.265 vs 1.221 ms/step at
-                # W=2), so each rank clears its own arena; in multimem mode the owner's multicast store already did it
+            if not remote_clear:
+                # clearing remotely doubles the NVLink stores (P2P pointers: measured 1.265 vs 1.221 ms/step at W=2;
+                # multicast: every rank would receive a second arena's worth of zeros), so each rank clears its own arena
                 self.arena.grad.zero_()
             self.allreduce_count += 1
             self._grads_clean = True
