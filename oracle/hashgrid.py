@@ -100,7 +100,7 @@ def lower_corner_mask(dim: int) -> torch.Tensor:
 def spatial_hash(corner_index: torch.Tensor, rows: int) -> torch.Tensor:
     """encoding.py:69-78 - int64 emulation of a uint32 multiply/xor hash, then % rows."""
     dim = corner_index.shape[-1]
-    primes = torch.tensor(HASH_PRIMES[:dim], dtype=torch.int64)
+    primes = torch.tensor(HASH_PRIMES[:dim], dtype=torch.int64, device=corner_index.device)
     mixed = (corner_index * primes) & 0xFFFFFFFF
     acc = mixed[..., 0].clone()
     for axis in range(1, dim):
@@ -111,7 +111,7 @@ def spatial_hash(corner_index: torch.Tensor, rows: int) -> torch.Tensor:
 def _scale(x: torch.Tensor, resolution: Sequence[int], anisotropic: bool) -> torch.Tensor:
     # V1 multiplies by a python int (encoding.py:111), V2 by an f32 vector (encoding.py:205,245).
     if anisotropic:
-        return x * torch.tensor([float(r) for r in resolution], dtype=torch.float32)
+        return x * torch.tensor([float(r) for r in resolution], dtype=torch.float32, device=x.device)
     return x * resolution[0]
 
 
@@ -125,7 +125,7 @@ def corners(x: torch.Tensor, level: Level, anisotropic: bool = False):
     xs = _scale(x, level.resolution, anisotropic)
     cell = xs.long()
     frac = xs - cell.float()
-    mask = lower_corner_mask(dim).reshape((1,) * (x.dim() - 1) + (1 << dim, dim))
+    mask = lower_corner_mask(dim).to(x.device).reshape((1,) * (x.dim() - 1) + (1 << dim, dim))
     cell = cell.unsqueeze(-2)
     frac = frac.unsqueeze(-2)
     index = torch.where(mask, cell, cell + 1)

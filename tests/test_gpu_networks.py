@@ -346,3 +346,53 @@ def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(dim, act):
         with torch.no_grad():
             y_eval = net(xd)
         assert torch.equal(y_mod.detach(), y) and torch.equal(y_eval, y)
+
+
+def test_eager_pytorch_on_the_same_gpu_is_the_comparator_not_the_product():
+    """the reference's PyTorch arithmetic (oracle port) run eagerly on the B200 next to the CUDA path, same
+    G4 + 2x64 model and batch; reported (gpurun_out/eager_comparator.json when that directory exists), and the
+    kernel path has to be well ahead of it."""
+    import json
+    import os
+    from mri_interpolation_b200 import models
+    from oracle import networks
+    g4 = dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, finest_resolution=2489)
+    n = 1 << 17
+    torch.manual_seed(1337)
+    net = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, batch_norm=False, lr=5e-3, **g4).to(DEV)
+    opt = net.configure_optimizers()
+    params, levels = networks.hashmlp_init(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, **g4)
+    params = {k: v.to(DEV).requires_grad_() for k, v in params.items() if not k.startswith("layers.")}
+    eager_opt = torch.optim.Adam(list(params.values()), lr=5e-3)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    x, y = torch.rand(n, 4, device=DEV, generator=gen), torch.rand(n, 1, device=DEV, generator=gen)
+
+    def ours():
+        loss = net.training_step((x, y), 0)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+
+    def eager():
+        eager_opt.zero_grad()
+        F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, False)).backward()
+        eager_opt.step()
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    t_ours, t_eager = timed(ours, 20), timed(eager, 5)
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/eager_comparator.json", "w") as f:
+            json.dump({"coords_per_step": n, "ms_per_step_cuda_path": t_ours, "ms_per_step_eager_pytorch_same_gpu": t_eager,
+                       "coords_per_s_cuda_path": n / t_ours * 1e3, "coords_per_s_eager_pytorch_same_gpu": n / t_eager * 1e3}, f)
+    assert t_ours * 3 < t_eager, (t_ours, t_eager)
