@@ -28,28 +28,50 @@ def slab_range(total: int, rank: int, world_size: int) -> Tuple[int, int]:
     return first, last - first
 
 
+def fold_batchnorm(lin: nn.Linear, bn: Optional[nn.BatchNorm1d]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(weight, bias) of the Linear with an eval-mode BatchNorm1d folded in: BN(z) = (z - mean) / sqrt(var + eps) * gamma
+    + beta is affine once the running statistics are frozen, so Linear -> BN is one Linear."""
+    w, b = lin.weight, lin.bias
+    if bn is None:
+        return w, b
+    scale = torch.rsqrt(bn.running_var + bn.eps)
+    if bn.weight is not None:
+        scale = scale * bn.weight
+    shift = bn.bias if bn.bias is not None else torch.zeros_like(scale)
+    return w * scale[:, None], (b - bn.running_mean) * scale + shift
+
+
 def _fused_plan(model) -> Optional[dict]:
-    """Describe the model for mri_hashmlp_sweep if it fits the fused kernel, else None."""
+    """Describe the model for mri_hashmlp_sweep if it fits the fused kernel, else None.
+
+    Decoder blocks may be Linear -> act [-> Dropout] (notebook variant) or the shipped Linear -> BatchNorm1d -> act ->
+    Dropout (models.py:718-739); the latter only in eval mode with running statistics, where BN folds into the Linear."""
     if not isinstance(model, HashMLP) or len(model.decoder) != 2:
         return None
     enc = model.encoder
     if getattr(enc, "_resolutions", None) is None or enc.n_features_per_level not in (1, 2, 4):
         return None
-    acts = []
+    acts, lins = [], []
     for blk in model.decoder:
         mods = list(blk)
-        if not isinstance(mods[0], nn.Linear) or len(mods) < 2:
+        if not isinstance(mods[0], nn.Linear) or mods[0].bias is None or len(mods) < 2:
             return None
-        a = _fusable_activation(mods[1])
-        if a is None or any(not (isinstance(m, nn.Dropout)) for m in mods[2:]):
+        bn, rest = None, mods[1:]
+        if isinstance(rest[0], nn.BatchNorm1d):
+            bn, rest = rest[0], rest[1:]
+            if model.training or bn.training or bn.running_mean is None or not rest:
+                return None
+        a = _fusable_activation(rest[0])
+        if a is None or any(not isinstance(m, nn.Dropout) or (m.training and m.p > 0.0) for m in rest[1:]):
             return None
         acts.append(a)
-    l0, l1 = model.decoder[0][0], model.decoder[1][0]
-    if l1.out_features != 1 or l0.out_features not in (16, 32, 64, 128) or l0.bias is None or l1.bias is None:
+        lins.append((mods[0], bn))
+    (l0, _), (l1, _) = lins
+    if l1.out_features != 1 or l0.out_features not in (16, 32, 64, 128):
         return None
     if acts[0] not in (_lib.ACT_GELU, _lib.ACT_RELU):
         return None  # the fused kernel is compiled for GELU / ReLU hidden activations
-    return dict(acts=acts, l0=l0, l1=l1)
+    return dict(acts=acts, l0=l0, l1=l1, blocks=lins)
 
 
 @torch.no_grad()
@@ -78,7 +100,8 @@ def dense_sweep(model, shape: Sequence[int], batch_size: int = 1 << 20, norm_sir
             tables = enc.tables()
             enc._fwd_layout.refresh(tables, enc._resolutions, enc._rows)
             l0, l1 = plan["l0"], plan["l1"]
-            packed = torch.cat([l0.weight.reshape(-1), l0.bias.reshape(-1), l1.weight.reshape(-1), l1.bias.reshape(-1)])
+            (w0, b0), (w1, b1) = (fold_batchnorm(lin, bn) for lin, bn in plan["blocks"])
+            packed = torch.cat([w0.reshape(-1), b0.reshape(-1), w1.reshape(-1), b1.reshape(-1)]).contiguous()
             dims = (ctypes.c_int32 * 3)(l0.in_features, l0.out_features, 1)
             out = torch.empty((count, 1), device=device, dtype=torch.float32)
             _lib.call("mri_hashmlp_sweep", flat_axes.data_ptr(), cshape, len(shape), first, count,

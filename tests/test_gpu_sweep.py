@@ -187,3 +187,33 @@ def test_tensor_core_sweep_kernel_matches_model_forward_and_oracle(dim, shape):
     assert torch.equal(fused, unfused)  # same kernel arithmetic as the module's no-grad forward
     parts = [sweep.dense_sweep(net, shape, rank=r, world_size=5) for r in range(5)]
     assert torch.equal(torch.cat(parts), fused)
+
+
+@pytest.mark.parametrize("n_levels", [16, 5])
+def test_fused_sweep_folds_eval_batchnorm_of_the_shipped_decoder(n_levels):
+    """The shipped HashMLP decoder (Linear -> BatchNorm1d -> GELU -> Dropout, models.py:718-739) in eval mode: BN folds
+    into the Linear, so the fused sweep kernels (tensor-core for L=16, CUDA-core otherwise) serve it too."""
+    from mri_interpolation_b200 import models, sweep
+    torch.manual_seed(4)
+    net = models.HashMLP(dim_in=3, n_levels=n_levels, n_features_per_level=2, log2_hashmap_size=12, base_resolution=8,
+                         finest_resolution=128, dim_hidden=64, dim_out=1, n_layers=2, dropout=0.1)
+    gen = torch.Generator().manual_seed(8)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.3)
+        for blk in net.decoder:
+            bn = blk[1]
+            assert isinstance(bn, torch.nn.BatchNorm1d)
+            bn.running_mean.copy_(torch.randn(bn.num_features, generator=gen) * 0.2)
+            bn.running_var.copy_(torch.rand(bn.num_features, generator=gen) + 0.3)
+            bn.weight.copy_(torch.randn(bn.num_features, generator=gen))
+            bn.bias.copy_(torch.randn(bn.num_features, generator=gen) * 0.1)
+    net = net.to(DEV)
+    net.train()
+    assert sweep._fused_plan(net) is None  # batch statistics in training mode: not foldable
+    shape = (19, 18, 7)
+    fused = sweep.dense_sweep(net, shape)
+    unfused = sweep.dense_sweep(net, shape, batch_size=999, fused=False)
+    assert net.training  # dense_sweep restores the mode
+    assert rel_err(fused, unfused) < 1e-5
+    assert float(fused.abs().max()) > 1e-3

@@ -224,3 +224,26 @@ def test_metrics_module():
     b = np.clip(a + rng.normal(0, 0.05, a.shape).astype(np.float32), 0, 1)
     assert metrics.structural_similarity(a, b) == pytest.approx(osweep.ssim_slices(a, b), abs=1e-12)
     assert metrics.peak_signal_noise_ratio(a, b) == pytest.approx(osweep.psnr(a, b), abs=1e-12)
+
+
+def test_fold_batchnorm_equals_linear_then_eval_batchnorm():
+    """sweep.fold_batchnorm: Linear -> BatchNorm1d(eval) collapses into one Linear (the shipped HashMLP decoder blocks,
+    models.py:718-739, take the fused sweep kernel this way)."""
+    import torch
+    from torch import nn
+    from mri_interpolation_b200.sweep import fold_batchnorm
+    torch.manual_seed(3)
+    for affine in (True, False):
+        lin, bn = nn.Linear(32, 64), nn.BatchNorm1d(64, affine=affine)
+        with torch.no_grad():
+            bn.running_mean.copy_(torch.randn(64) * 0.3)
+            bn.running_var.copy_(torch.rand(64) + 0.2)
+            if affine:
+                bn.weight.copy_(torch.randn(64))
+                bn.bias.copy_(torch.randn(64))
+        bn.eval()
+        x = torch.randn(100, 32)
+        w, b = fold_batchnorm(lin, bn)
+        torch.testing.assert_close(torch.nn.functional.linear(x, w, b), bn(lin(x)), rtol=1e-5, atol=1e-5)
+    w, b = fold_batchnorm(lin, None)
+    assert w is lin.weight and b is lin.bias
