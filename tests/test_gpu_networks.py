@@ -265,13 +265,24 @@ def test_sharded_adam_kernel_emulated_two_ranks_on_one_gpu():
     assert torch.equal(params[0], params[1])
 
 
-def test_fused_hashdecoder_backward_matches_unfused_and_oracle():
+# geometries of the fused encoder+decoder kernels: all-T levels; coarse levels with non-power-of-two row counts
+# (res^D < T: the `%` wrap); anisotropic V2 levels (max(res)^D rows)
+FUSED_GEOMETRIES = [
+    dict(dim_in=4, log2_hashmap_size=12, base_resolution=16, finest_resolution=200),
+    dict(dim_in=4, log2_hashmap_size=16, base_resolution=8, finest_resolution=300),
+    dict(dim_in=3, log2_hashmap_size=14, base_resolution=8, finest_resolution=300),
+    dict(dim_in=3, log2_hashmap_size=13, base_resolution=(8, 6, 4), finest_resolution=(200, 150, 40)),
+]
+
+
+@pytest.mark.parametrize("geo", FUSED_GEOMETRIES)
+def test_fused_hashdecoder_backward_matches_unfused_and_oracle(geo):
     """G4-shaped model (L=16, F=2, hidden 64): encoder+decoder backward in one kernel vs the two-kernel path vs the oracle."""
     import copy
     from mri_interpolation_b200 import models
     from oracle import networks
-    kw = dict(dim_in=4, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=200,
-              dim_hidden=64, dim_out=1, n_layers=2)
+    dim = geo["dim_in"]
+    kw = dict(n_levels=16, n_features_per_level=2, dim_hidden=64, dim_out=1, n_layers=2, **geo)
     torch.manual_seed(1337)
     net = models.HashMLP(**kw, batch_norm=False)
     gen = torch.Generator().manual_seed(1)
@@ -279,14 +290,18 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle():
         for lv in net.encoder.levels:
             lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
     params = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items() if not k.startswith("layers.")}
-    levels = networks.hashgrid.geometry(4, 16, 12, 16, 200)
+    levels = networks.hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
+    aniso = not isinstance(geo["base_resolution"], int)
+    if geo["log2_hashmap_size"] != 12:
+        assert any(lv.rows & (lv.rows - 1) for lv in levels)  # the non-power-of-two wrap is exercised
     for n in (1, 33, 5000):
-        x, y = torch.rand(n, 4, generator=gen), torch.rand(n, 1, generator=gen)
+        x, y = torch.rand(n, dim, generator=gen), torch.rand(n, 1, generator=gen)
         for p in params.values():
             p.grad = None
-        F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, False)).backward()
+        F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, aniso)).backward()
         fused, plain = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
         plain.fuse_backward = False
+        assert type(fused(x.to(DEV)).grad_fn).__name__.startswith("HashDecoderFn")
         lf = fused.training_step((x.to(DEV), y.to(DEV)), 0)
         lf.backward()
         lp = plain.training_step((x.to(DEV), y.to(DEV)), 0)
@@ -303,14 +318,16 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle():
                 assert rel_err(pf.grad, ref) < 1e-3, (n, name)
 
 
-@pytest.mark.parametrize("dim,act", [(4, "gelu"), (3, "relu")])
-def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(dim, act):
+@pytest.mark.parametrize("geo,act", [(FUSED_GEOMETRIES[0], "gelu"), (FUSED_GEOMETRIES[1], "relu"), (FUSED_GEOMETRIES[2], "relu"),
+                                     (FUSED_GEOMETRIES[3], "gelu")])
+def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(geo, act):
     """Encoder+decoder forward in ONE kernel (mri_hashdecoder_forward): the encoding it writes is bit-identical to
     mri_hashgrid_forward, the output equals the gather + decoder kernels and the oracle."""
     from mri_interpolation_b200 import _lib, functional as Fn, models
     from oracle import hashgrid, networks
-    kw = dict(dim_in=dim, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=300,
-              dim_hidden=64, dim_out=1, n_layers=2)
+    dim = geo["dim_in"]
+    aniso = not isinstance(geo["base_resolution"], int)
+    kw = dict(n_levels=16, n_features_per_level=2, dim_hidden=64, dim_out=1, n_layers=2, **geo)
     torch.manual_seed(7)
     net = models.HashMLP(**kw, batch_norm=False, activation=torch.nn.ReLU if act == "relu" else torch.nn.GELU)
     gen = torch.Generator().manual_seed(3)
@@ -318,7 +335,7 @@ def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(dim, act):
         for lv in net.encoder.levels:
             lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
     params = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    levels = hashgrid.geometry(dim, 16, 12, 16, 300)
+    levels = hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
     net = net.to(DEV)
     enc_mod = net.encoder
     l1, l2, a1, a2 = net._fused_decoder_plan()
@@ -339,7 +356,7 @@ def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(dim, act):
                   enc.data_ptr(), y.data_ptr(), pre2.data_ptr(), _lib.stream())
         assert torch.equal(enc, enc_ref), n
         torch.testing.assert_close(y, y_two, rtol=1e-6, atol=1e-7)
-        ref = networks.hashmlp_forward(x, params, levels, 2, False, F.relu if act == "relu" else F.gelu)
+        ref = networks.hashmlp_forward(x, params, levels, 2, aniso, F.relu if act == "relu" else F.gelu)
         assert float((y.cpu() - ref).abs().max()) < 1e-3 * (float(ref.abs().max()) + 1e-6), n
         # module path: training forward keeps enc for the backward, no-grad forward writes only y
         y_mod = net(xd)
