@@ -212,6 +212,13 @@ int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t
                   double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                   int zero_grad, void* stream);
 
+/* The same step for CUDA-graph capture: the 1-based step counter lives in device memory (*step_dev, int64) and is
+ * advanced by the call itself (a one-thread kernel that also evaluates the bias corrections in double into
+ * hyper_dev[0..1]), so a captured training step can be replayed without host-side arguments going stale. */
+int mri_adam_step_captured(float* p, float* g, float* m, float* v, int64_t count, int64_t* step_dev, float* hyper_dev,
+                           double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                           int zero_grad, void* stream);
+
 /* Data-parallel variant of the step above, ONE kernel per rank over NVLink peer memory: for its shard
  * [shard_begin, shard_begin + shard_len) of the flat arena the rank sums the gradients of all `world` ranks by
  * loading their gradient arenas directly (host_peer_grads[r] = device pointer of rank r's arena, P2P-mapped, e.g.

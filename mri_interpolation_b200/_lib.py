@@ -50,6 +50,7 @@ SIGNATURES = {
     "mri_dense_backward": [_P, _I64, _P, _P, _P, _I64, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "mri_mse_loss_grad": [_P, _P, _I64, _F, _P, _P, _P],
     "mri_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _I, _P],
+    "mri_adam_step_captured": [_P, _P, _P, _P, _I64, _P, _P, _D, _D, _D, _D, _D, _D, _I, _P],
     "mri_adam_step_sharded": [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_uint64,
                               _I, _I, _P, _P, _I64, _I64, _I64,
                               _D, _D, _D, _D, _D, _D, _I, _P],

@@ -30,8 +30,24 @@ __device__ __forceinline__ void adam_update(float& p, float& g, float& m, float&
   if (a.zero_grad) g = 0.0f;
 }
 
+// CUDA-graph friendly step counter: lives in device memory and is advanced by the launch itself, so a captured
+// step can be replayed; the bias corrections are evaluated in double like the host path.
+__global__ void adam_hyper_kernel(int64_t* __restrict__ step, float* __restrict__ hyper, double lr, double beta1, double beta2) {
+  const int64_t t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(t));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(t));
+  hyper[0] = static_cast<float>(lr / bc1);
+  hyper[1] = static_cast<float>(sqrt(bc2));
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, int64_t n4, int64_t n, AdamArgs a) {
+                                                   float* __restrict__ v, int64_t n4, int64_t n, AdamArgs a,
+                                                   const float* __restrict__ hyper) {
+  if (hyper != nullptr) {  // {lr / bc1, sqrt(bc2)} written by adam_hyper_kernel earlier on this stream
+    a.step_size = __ldg(hyper);
+    a.bc2_sqrt = __ldg(hyper + 1);
+  }
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -204,21 +220,13 @@ extern "C" int mri_mse_loss_grad(const float* pred, const float* target, int64_t
   return MRI_OK;
 }
 
-extern "C" int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t step, double lr,
-                             double beta1, double beta2, double eps, double weight_decay, double grad_scale,
-                             int zero_grad, void* stream) {
-  if (!p || !g || !m || !v) return fail(MRI_ERR_INVALID, "adam: null pointer");
-  if (count < 0 || step < 1) return fail(MRI_ERR_INVALID, "adam: count must be >= 0 and step >= 1");
-  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-       reinterpret_cast<uintptr_t>(v)) & 15)
-    return fail(MRI_ERR_INVALID, "adam: arenas must be 16-byte aligned");
-  if (count == 0) return MRI_OK;
-  // bias corrections in double, like torch's python-float arithmetic
-  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
-  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+namespace {
+int launch_adam(float* p, float* g, float* m, float* v, int64_t count, double step_size, double bc2_sqrt, double beta1,
+                double beta2, double eps, double weight_decay, double grad_scale, int zero_grad, const float* hyper,
+                cudaStream_t stream) {
   AdamArgs a;
-  a.step_size = static_cast<float>(lr / bc1);
-  a.bc2_sqrt = static_cast<float>(sqrt(bc2));
+  a.step_size = static_cast<float>(step_size);
+  a.bc2_sqrt = static_cast<float>(bc2_sqrt);
   a.beta1 = static_cast<float>(beta1);
   a.beta2 = static_cast<float>(beta2);
   a.one_minus_beta1 = static_cast<float>(1.0 - beta1);
@@ -232,7 +240,44 @@ extern "C" int mri_adam_step(float* p, float* g, float* m, float* v, int64_t cou
   if (want < 1) want = 1;
   const int64_t cap = 8LL * sm_count();
   const int grid = static_cast<int>(want < cap ? want : cap);
-  adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n4, count, a);
+  adam_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, n4, count, a, hyper);
   MRI_LAUNCH_OK("adam_kernel");
   return MRI_OK;
+}
+
+int check_adam_arenas(const float* p, const float* g, const float* m, const float* v, int64_t count) {
+  if (!p || !g || !m || !v) return fail(MRI_ERR_INVALID, "adam: null pointer");
+  if (count < 0) return fail(MRI_ERR_INVALID, "adam: count must be >= 0");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15)
+    return fail(MRI_ERR_INVALID, "adam: arenas must be 16-byte aligned");
+  return MRI_OK;
+}
+}  // namespace
+
+extern "C" int mri_adam_step(float* p, float* g, float* m, float* v, int64_t count, int64_t step, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                             int zero_grad, void* stream) {
+  int st = check_adam_arenas(p, g, m, v, count);
+  if (st != MRI_OK) return st;
+  if (step < 1) return fail(MRI_ERR_INVALID, "adam: step must be >= 1");
+  if (count == 0) return MRI_OK;
+  // bias corrections in double, like torch's python-float arithmetic
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  return launch_adam(p, g, m, v, count, lr / bc1, sqrt(bc2), beta1, beta2, eps, weight_decay, grad_scale, zero_grad, nullptr,
+                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mri_adam_step_captured(float* p, float* g, float* m, float* v, int64_t count, int64_t* step_dev,
+                                      float* hyper_dev, double lr, double beta1, double beta2, double eps,
+                                      double weight_decay, double grad_scale, int zero_grad, void* stream) {
+  int st = check_adam_arenas(p, g, m, v, count);
+  if (st != MRI_OK) return st;
+  if (!step_dev || !hyper_dev) return fail(MRI_ERR_INVALID, "adam_captured: null step/hyper buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  adam_hyper_kernel<<<1, 1, 0, s>>>(step_dev, hyper_dev, lr, beta1, beta2);  // advances the counter even for count == 0
+  MRI_LAUNCH_OK("adam_hyper_kernel");
+  if (count == 0) return MRI_OK;
+  return launch_adam(p, g, m, v, count, 0.0, 1.0, beta1, beta2, eps, weight_decay, grad_scale, zero_grad, hyper_dev, s);
 }

@@ -152,6 +152,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._grads_clean = True  # freshly allocated arena gradient is zero
         self.allreduce_count = 0
         self._overlap = None
+        self._step_dev = None   # device-side step counter + {lr/bc1, sqrt(bc2)} scratch: set by use_device_step()
+        self._hyper_dev = None
 
     # -- distributed
     def _world(self) -> int:
@@ -263,12 +265,50 @@ class FusedAdam(torch.optim.Optimizer):
             raise MriB200Error("FusedAdam: a sharded optimiser cannot step with data_parallel switched off")
         scale = self.sync_gradients()
         self.step_count += 1
-        _lib.call("mri_adam_step", self.arena.data.data_ptr(), self.arena.grad.data_ptr(), self.exp_avg.data_ptr(),
-                  self.exp_avg_sq.data_ptr(), self.arena.numel, self.step_count, float(g["lr"]), float(g["betas"][0]),
-                  float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(scale),
-                  1 if self.fuse_zero_grad else 0, _lib.stream())
+        if self._step_dev is not None:
+            # CUDA-graph friendly: the counter is advanced on the device by the launch itself (replayable)
+            _lib.call("mri_adam_step_captured", self.arena.data.data_ptr(), self.arena.grad.data_ptr(),
+                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.arena.numel, self._step_dev.data_ptr(),
+                      self._hyper_dev.data_ptr(), float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                      float(g["weight_decay"]), float(scale), 1 if self.fuse_zero_grad else 0, _lib.stream(), kernels=2)
+        else:
+            _lib.call("mri_adam_step", self.arena.data.data_ptr(), self.arena.grad.data_ptr(), self.exp_avg.data_ptr(),
+                      self.exp_avg_sq.data_ptr(), self.arena.numel, self.step_count, float(g["lr"]), float(g["betas"][0]),
+                      float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), float(scale),
+                      1 if self.fuse_zero_grad else 0, _lib.stream())
         self._grads_clean = bool(self.fuse_zero_grad)
         return loss
+
+    # -- CUDA-graph support (single GPU): see graph.GraphedTrainStep
+    def use_device_step(self) -> None:
+        """Keep the step counter in device memory from now on, so that step() can be captured in a CUDA graph and
+        replayed (host-side bias corrections would be frozen into the graph).  lr/betas/eps are captured by value."""
+        if self._world() > 1:
+            raise MriB200Error("FusedAdam: CUDA-graph capture of the optimiser step is single-GPU only")
+        if self._step_dev is None:
+            dev = self.arena.data.device
+            self._step_dev = torch.full((1,), self.step_count, dtype=torch.int64, device=dev)
+            self._hyper_dev = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    def note_replayed_step(self) -> None:
+        """A captured step() was replayed: keep the host-side mirror of the step counter in sync."""
+        self.step_count += 1
+        self._grads_clean = bool(self.fuse_zero_grad)
+
+    def snapshot(self):
+        """Clones of everything a step mutates (parameters, gradients, moments, counter)."""
+        return (self.arena.data.clone(), self.arena.grad.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(),
+                self.step_count, self._grads_clean)
+
+    def restore(self, snap) -> None:
+        data, grad, m, v, count, clean = snap
+        self.arena.data.copy_(data)
+        self.arena.grad.copy_(grad)
+        self.exp_avg.copy_(m)
+        self.exp_avg_sq.copy_(v)
+        self.step_count, self._grads_clean = count, clean
+        if self._step_dev is not None:
+            self._step_dev.fill_(count)
 
     def zero_grad(self, set_to_none: bool = False):
         """Gradients stay views of the arena.  The first zero_grad() after a fused step is free (the
@@ -284,6 +324,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        if self._step_dev is not None:
+            self._step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
         for k, v in sd["param_groups"][0].items():

@@ -174,7 +174,8 @@ class Trainer:
     def __init__(self, accelerator: str = "auto", devices: Any = "auto", max_epochs: Optional[int] = None,
                  accumulate_grad_batches: Any = None, precision: Any = 32, logger: Any = True,
                  default_root_dir: Optional[str] = None, enable_progress_bar: bool = False, max_steps: int = -1,
-                 callbacks: Optional[list] = None, gpus: Any = None, enable_checkpointing: bool = True, **kwargs):
+                 callbacks: Optional[list] = None, gpus: Any = None, enable_checkpointing: bool = True,
+                 cuda_graph: Optional[bool] = None, **kwargs):
         if str(precision) not in ("32", "32-true"):
             raise NotImplementedError("the B200 backend trains in fp32 (launcher.py:162 precision=32)")
         self.accelerator = accelerator
@@ -183,6 +184,10 @@ class Trainer:
         self.accumulate_grad_batches = accumulate_grad_batches
         self.enable_progress_bar = enable_progress_bar
         self.enable_checkpointing = enable_checkpointing
+        # replay the whole training step as one CUDA graph (graph.GraphedTrainStep): for the reference's small batches
+        # (4 096 / 10 000 coordinates) the step is host-bound otherwise.  None -> the MRI_CUDA_GRAPH environment switch
+        self.cuda_graph = (os.environ.get("MRI_CUDA_GRAPH", "0") == "1") if cuda_graph is None else bool(cuda_graph)
+        self.graphed_steps = 0
         root = default_root_dir or os.getcwd()
         if logger is True:
             self.logger = _Logger(save_dir=root)
@@ -264,6 +269,11 @@ class Trainer:
         model.on_train_start()
         t0 = time.time()
         stop = False
+        graphed = None
+        distributed = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1
+        can_graph = (self.cuda_graph and device.type == "cuda" and not distributed
+                     and hasattr(self.optimizer, "use_device_step"))
         for epoch in range(self.max_epochs):
             self.current_epoch = epoch
             accum = self._accum_factor(epoch)
@@ -272,6 +282,22 @@ class Trainer:
             pending = 0
             for batch_idx, batch in enumerate(train_dataloaders):
                 batch = _move(batch, device)
+                if can_graph and accum == 1:
+                    if graphed is None and isinstance(batch, (tuple, list)) and all(isinstance(t, torch.Tensor) for t in batch):
+                        from .graph import GraphedTrainStep
+                        graphed = GraphedTrainStep(model, self.optimizer, batch)
+                    if graphed is not None and graphed.matches(batch):
+                        graphed(batch)
+                        for name, value in graphed.logged.items():
+                            self._record(name, value)
+                        self.graphed_steps += 1
+                        self.global_step += 1
+                        if self.global_step % 50 == 0:
+                            self._flush()
+                        if 0 < self.max_steps <= self.global_step:
+                            stop = True
+                            break
+                        continue
                 loss = model.training_step(batch, batch_idx)
                 if isinstance(loss, dict):
                     loss = loss["loss"]
