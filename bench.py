@@ -101,22 +101,31 @@ class ClockSampler:
             import tempfile
             fd, self.path = tempfile.mkstemp(prefix="mri_clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MRI_BENCH_CLOCK_MS", "50")],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MRI_BENCH_CLOCK_MS", "20")],
                                          stdout=fd, stderr=subprocess.DEVNULL)
             os.close(fd)
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def mark(self):
+        """Start of the window of interest: samples written before this call are dropped by stop()."""
+        self.skip = 0
+        if self.proc is not None:
+            try:
+                self.skip = len(open(self.path).read().splitlines())
+            except Exception:  # noqa: BLE001
+                self.skip = 0
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
         try:
-            lines = open(self.path).read().splitlines()
+            lines = open(self.path).read().splitlines()[getattr(self, "skip", 0):]
             os.unlink(self.path)
         except Exception:  # noqa: BLE001
             lines = []
@@ -321,14 +330,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # nvidia-smi needs a few hundred ms to come up: started before the untimed steps, marked below
     for i in range(PRIMING_STEPS):  # untimed: lets torch's caching allocator reach its steady state (no cudaMalloc later)
         step(i)
     for i in range(args.warmup):
         step(i)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
+    clocks.mark()
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -358,6 +368,26 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+    # a timed region shorter than nvidia-smi's sampling period holds no clock sample: run the same steps again, untimed,
+    # for ~0.5 s on every rank (same count everywhere: the steps are collective) and sample the clocks under that load
+    need_probe = torch.tensor([1 if (rank == 0 and clk is not None and clk.get("samples") == 0 and
+                                     "nvidia-smi unavailable" not in clk.get("reasons", []) and
+                                     os.environ.get("MRI_BENCH_NO_CLOCKS") != "1") else 0], device=dev)
+    if world > 1:
+        dist.broadcast(need_probe, src=0)
+    if int(need_probe.item()):
+        probe = ClockSampler(local_rank)
+        if rank == 0:
+            probe.start()
+            time.sleep(0.4)
+        barrier()
+        probe.mark()
+        for i in range(total_steps, total_steps + max(20, int(500.0 / max(ms_step, 1e-3)))):
+            step(i)
+        barrier()
+        if rank == 0:
+            clk = probe.stop()
+            clk["window"] = "identical untimed steps run right after the timed region (it was shorter than one sample)"
     value = n * world / (ms_step * 1e-3)
     final_loss = float(loss.detach())
 
