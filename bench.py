@@ -316,6 +316,10 @@ def main():
     # the shuffled index stream is drawn up front (like a DataLoader sampler), as a ring of 32 batches
     ring = 32
     index = torch.randint(0, sampler.total, (ring, n), device=dev, generator=gen)
+    batch_order = os.environ.get("MRI_BATCH_ORDER", "blk4")
+    if batch_order != "none":
+        from mri_interpolation_b200 import functional as Fn
+        index = Fn.locality_sort(index, info["shape"], block=int(batch_order[3:]) if batch_order.startswith("blk") else 1)
 
     def step(i):
         x, y = sampler.batch(index[i % ring])

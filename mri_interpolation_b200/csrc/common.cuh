@@ -1,6 +1,7 @@
 // Shared device/host helpers for the sm_100a kernels behind include/mri_b200.h.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -14,6 +15,22 @@ char* error_buffer();
 int fail(int status, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int sm_count();
+
+// One-time per-DEVICE kernel setup (dynamic shared-memory attribute, occupancy query): function attributes and
+// occupancy belong to the device that is current at the call, so the cache is indexed by device id.  The cached
+// computations are idempotent, so concurrent first calls from several host threads are benign.
+constexpr int MRI_MAX_DEVICES = 64;
+struct DeviceCache {
+  std::atomic<int> slot[MRI_MAX_DEVICES];
+  DeviceCache() {
+    for (auto& s : slot) s.store(0, std::memory_order_relaxed);
+  }
+  static int device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MRI_MAX_DEVICES) d = 0;
+    return d;
+  }
+};
 
 #define MRI_CUDA_OK(expr)                                   \
   do {                                                      \

@@ -107,5 +107,77 @@ __device__ __forceinline__ void scatter_half_level(const Cell<D>& cell, int b0, 
   }
 }
 
+// ---- run merging for locality-ordered batches -------------------------------------------------------
+// A batch ordered along axis 0 (functional.locality_sort: voxels of one axis-0 line are neighbours, axis-0 index
+// ascending) puts samples that differ ONLY in their axis-0 coordinate into consecutive rows of an m-tile.  At a coarse
+// level several of them fall into the same or into adjacent axis-0 cells, so their lower/upper corners are the SAME
+// table rows for every one of the 2^(D-1) corner combinations of the other axes - and those combinations' weights are
+// bit-identical too (same coordinates).  red.global.add does not merge identical addresses inside an instruction (ncu:
+// every duplicate is its own L2 sector operation), so the duplicates are summed in registers first:
+//   * lanes are laid out as in the fused kernels: lane = 4 g + t, row g of an 8-row group, t & 1 = axis-0 half
+//   * `kk` = axis-0 cell index this lane updates (lower cell + half), `line_mask` bit (4g + t) = rows g and g+1 are live
+//     and agree bit-for-bit on every coordinate but axis 0
+//   * contiguous rows with equal kk form a run whose first lane (the head) ends up with the run's sum (3 doubling
+//     steps); then the head of a lower-half run absorbs the upper-half run that ends on the previous row when that run
+//     updates the same cell (cell(g-1) + 1 == cell(g)), and the absorbed run issues nothing.
+// Works for ANY input order: rows that do not form contiguous runs simply stay separate (correct, just not merged).
+struct MergedHalf {
+  float v0, v1;
+  bool active;
+};
+__device__ __forceinline__ MergedHalf merge_line_runs(uint32_t kk, float v0, float v1, bool live, uint32_t line_mask, int lane) {
+  constexpr uint32_t full = 0xffffffffu;
+  const int g = lane >> 2, t = lane & 3, b0 = t & 1;
+  const uint32_t kk_next = __shfl_down_sync(full, kk, 4);
+  const bool eq = ((line_mask >> lane) & 1u) && kk_next == kk;  // line_mask has no bits for g == 7
+  const uint32_t m = __ballot_sync(full, eq);
+  const uint32_t col = (m >> t) & 0x11111111u;                  // bit 4g': row g' continues into row g'+1 (my level, my half)
+  const int cnt = (__ffs(~((col >> (4 * g)) | 0xEEEEEEEEu)) - 1) >> 2;  // rows after mine in my run
+  const bool head = g == 0 || !((col >> (4 * (g - 1))) & 1u);
+#pragma unroll
+  for (int d = 1; d <= 4; d <<= 1) {
+    const float a0 = __shfl_down_sync(full, v0, 4 * d), a1 = __shfl_down_sync(full, v1, 4 * d);
+    if (d <= cnt) { v0 += a0; v1 += a1; }
+  }
+  // link between an upper-half run ending on row e and the lower-half run starting on row e+1
+  const int e = g + cnt;
+  const bool can = b0 ? (e < 7) : (g > 0);
+  const int key_src = can ? (b0 ? 4 * (e + 1) + (t - 1) : lane - 3) : lane;
+  const uint32_t kk_x = __shfl_sync(full, kk, key_src);
+  const int line_bit = b0 ? 4 * e + t : (g > 0 ? lane - 4 : 0);
+  const bool link = can && ((line_mask >> line_bit) & 1u) && kk_x == kk;
+  // head lane of the upper-half run that contains row g-1 (column t | 1)
+  const int gm1 = g > 0 ? g - 1 : 0;
+  const uint32_t colp = (m >> (t | 1)) & 0x11111111u;
+  const uint32_t below = ~colp & 0x11111111u & ((1u << (4 * gm1)) - 1u);
+  const int s = below ? ((31 - __clz(below)) >> 2) + 1 : 0;
+  const int v_src = (link && !b0) ? 4 * s + (t | 1) : lane;
+  const float p0 = __shfl_sync(full, v0, v_src), p1 = __shfl_sync(full, v1, v_src);
+  if (link && !b0) { v0 += p0; v1 += p1; }
+  MergedHalf r;
+  r.v0 = v0; r.v1 = v1;
+  r.active = live && head && !(b0 && link);
+  return r;
+}
+
+// scatter of one (already merged) half level: F = 2, value (v0, v1) carries the axis-0 weight
+template <int D, bool POW2>
+__device__ __forceinline__ void scatter_half_level_merged(const Cell<D>& cell, int b0, const LevelDev& lv, float* tbl, float v0, float v1) {
+  constexpr int CH = 1 << (D - 1);
+  const uint32_t t0 = cell.lo[0] + static_cast<uint32_t>(b0);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    uint32_t h = t0;
+    float w = 1.0f;
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const bool up = (c >> (d - 1)) & 1;
+      h ^= up ? (cell.lo[d] + prime(d)) : cell.lo[d];
+      const float wd = up ? cell.wu[d] : cell.wl[d];
+      w = d == 1 ? wd : __fmul_rn(w, wd);
+    }
+    red_add_v2(tbl + static_cast<size_t>(wrap_rows<POW2>(h, lv)) * 2, v0 * w, v1 * w);
+  }
+}
 
 }  // namespace mri

@@ -1,0 +1,363 @@
+// Backward of the whole HashMLP in ONE kernel: decoder backward on the tensor cores (decoder.cu's
+// decoder2_mma_bwd_kernel arithmetic) with the hash-table scatter fused in (autograd of models.py:741-744 on top of
+// encoding.py:127-128), for the headline geometry F = 2, L = 16 (K0 = 32), H = 64, D = 3 / 4.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "hash_device.cuh"
+#include "mma_device.cuh"
+
+namespace mri {
+namespace {
+
+// Same kernel with the table scatter fused in: the dEnc accumulator fragments (rows g / g+8, level 4*nt2 + t for
+// F = 2) never go to memory - lane pairs (t even / odd) exchange their two levels with one shuffle and then act as the
+// lower / upper axis-0 halves of the pair-lane scatter (hash_device.cuh), so the red.global.add traffic overlaps the
+// tensor-core and GELU work of the next tile.
+template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
+__global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(const float* __restrict__ enc, int64_t n,
+                                                                           const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                           const float* __restrict__ w2, const float* __restrict__ pre2,
+                                                                           const float* __restrict__ gy, int act2,
+                                                                           const float* __restrict__ x, const __grid_constant__ LevelTable T,
+                                                                           float* __restrict__ grad_tables, float* __restrict__ gw1,
+                                                                           float* __restrict__ gb1, float* __restrict__ gw2,
+                                                                           float* __restrict__ gb2) {
+  constexpr int WS = K0 + MMA_PAD;   // row stride of W1 / enc planes (bf16 elements)
+  constexpr int TS = H + MMA_PAD;    // row stride of W1^T / dPre1 planes
+  constexpr int NWARP = DEC_THREADS / 32;
+  extern __shared__ __align__(16) uint8_t msm[];
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(msm);   // [H][WS]
+  __nv_bfloat16* w_lo = w_hi + H * WS;
+  __nv_bfloat16* wt_hi = w_lo + H * WS;                           // [K0][TS]  (W1 transposed)
+  __nv_bfloat16* wt_lo = wt_hi + K0 * TS;
+  float* b1s = reinterpret_cast<float*>(wt_lo + K0 * TS);
+  float* w2s = b1s + H;
+  __nv_bfloat16* warp_base = reinterpret_cast<__nv_bfloat16*>(w2s + H);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  __nv_bfloat16* dp_hi = warp_base + warp * (2 * 32 * (TS + WS));  // [32][TS]
+  __nv_bfloat16* dp_lo = dp_hi + 32 * TS;
+  __nv_bfloat16* e_hi = dp_lo + 32 * TS;                            // [32][WS]
+  __nv_bfloat16* e_lo = e_hi + 32 * WS;
+
+  stage_planes<H, K0>(w1, w_hi, w_lo, false);
+  stage_planes<H, K0>(w1, wt_hi, wt_lo, true);
+  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+    b1s[e] = __ldg(b1 + e);
+    w2s[e] = __ldg(w2 + e);
+  }
+  // the lanes of one instruction work on two different levels: a lane-indexed read of the __grid_constant__ table is a
+  // replayed LDC on the long scoreboard (17 % of the stall samples in ncu) - shared memory serves it in one pass
+  __shared__ LevelDev lvs[K0 / 2];
+  if (threadIdx.x < K0 / 2) lvs[threadIdx.x] = T.lv[threadIdx.x];
+  __syncthreads();
+
+  float wacc[H / 16][K0 / 8][4];
+#pragma unroll
+  for (int a = 0; a < H / 16; ++a)
+#pragma unroll
+    for (int b = 0; b < K0 / 8; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) wacc[a][b][c] = 0.0f;
+  float pb1[H / 8][2], pw2[H / 8][2];
+#pragma unroll
+  for (int nt = 0; nt < H / 8; ++nt) { pb1[nt][0] = pb1[nt][1] = 0.0f; pw2[nt][0] = pw2[nt][1] = 0.0f; }
+  float pb2 = 0.0f;
+
+  // inputs of one 16-row m-tile as they come out of global memory; the next tile's are requested before the current
+  // tile is processed (2 warps per scheduler cannot hide a DRAM round trip per tile on their own)
+  struct TileIn {
+    float2 e[K0 / 16][2][2];  // [k-tile][8-column half][row g / g+8]
+    float gy[2], p2[2];
+    float xv[2][D];
+  };
+  auto fetch = [&](int64_t row0, TileIn& ti) {
+    const int64_t r[2] = {row0 + g, row0 + g + 8};
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const bool live = r[rr] < n;
+      load_coord<D>(x, live ? r[rr] : 0, ti.xv[rr]);
+      ti.gy[rr] = live ? __ldg(gy + r[rr]) : 0.0f;
+      ti.p2[rr] = live ? __ldg(pre2 + r[rr]) : 0.0f;
+#pragma unroll
+      for (int kt = 0; kt < K0 / 16; ++kt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          ti.e[kt][half][rr] = live ? __ldg(reinterpret_cast<const float2*>(enc + r[rr] * K0 + 16 * kt + 8 * half + 2 * t))
+                                    : make_float2(0.0f, 0.0f);
+    }
+  };
+
+  // Every warp walks its OWN contiguous range of 32-row chunks.  With a locality-ordered batch a grid-stride walk would
+  // make all resident warps work on neighbouring samples at the same time, i.e. reduce into the same few rows of the
+  // coarse levels at once - and the L2 serialises reductions on one address (measured: 2.2x slower when 8192 rows are
+  // hot grid-wide).  Warps that are far apart in the batch are far apart in the volume.
+  const int64_t chunks = (n + 31) / 32;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * NWARP;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * NWARP + warp;
+  const int64_t chunk_end = CONTIGUOUS ? ((wid + 1) * chunks) / n_warps : chunks;
+  const int64_t chunk_stride = CONTIGUOUS ? 1 : n_warps;
+  int64_t chunk = CONTIGUOUS ? (wid * chunks) / n_warps : wid;
+  TileIn nxt;
+  fetch(chunk * 32, nxt);
+  for (; chunk < chunk_end; chunk += chunk_stride) {
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const int64_t row0 = chunk * 32 + 16 * mt;
+      const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
+      const TileIn cur = nxt;
+      fetch(mt == 0 ? row0 + 16 : (chunk + chunk_stride) * 32, nxt);
+      float xv_lo[D], xv_hi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) { xv_lo[d] = cur.xv[0][d]; xv_hi[d] = cur.xv[1][d]; }
+      // rows g, g+1 of an 8-row group live and on one axis-0 line (identical coordinates on every other axis)
+      uint32_t line_mask[2] = {0u, 0u};
+      if constexpr (MERGE_NT2 > 0) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          bool same = g < 7 && (rr == 0 ? r_lo : r_hi) + 1 < n;
+#pragma unroll
+          for (int d = 1; d < D; ++d) {
+            const float mine = rr == 0 ? xv_lo[d] : xv_hi[d];
+            const float next = __shfl_down_sync(0xffffffffu, mine, 4);  // every lane takes part: no short-circuit around it
+            same = same && next == mine;
+          }
+          line_mask[rr] = __ballot_sync(0xffffffffu, same);
+        }
+      }
+      float acc[H / 8][4];
+      {
+        uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
+#pragma unroll
+        for (int kt = 0; kt < K0 / 16; ++kt)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
+            split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+          }
+#pragma unroll
+        for (int kt = 0; kt < K0 / 16; ++kt)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int col = 16 * kt + 8 * half + 2 * t;
+            *reinterpret_cast<uint32_t*>(e_hi + (16 * mt + g) * WS + col) = a_hi[kt][2 * half];
+            *reinterpret_cast<uint32_t*>(e_lo + (16 * mt + g) * WS + col) = a_lo[kt][2 * half];
+            *reinterpret_cast<uint32_t*>(e_hi + (16 * mt + g + 8) * WS + col) = a_hi[kt][2 * half + 1];
+            *reinterpret_cast<uint32_t*>(e_lo + (16 * mt + g + 8) * WS + col) = a_lo[kt][2 * half + 1];
+          }
+        hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
+      }
+      float dp2_lo = 0.0f, dp2_hi = 0.0f;
+      if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
+      if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
+      if (t == 0) pb2 += dp2_lo + dp2_hi;
+      uint32_t da_hi[H / 16][4], da_lo[H / 16][4];
+#pragma unroll
+      for (int nt = 0; nt < H / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float dp2 = e < 2 ? dp2_lo : dp2_hi;
+          float a, gp;
+          act_and_grad<ACT1>(acc[nt][e], a, gp);
+          pw2[nt][e & 1] = fmaf(dp2, a, pw2[nt][e & 1]);
+          const float dpre = dp2 * w2s[8 * nt + 2 * t + (e & 1)] * gp;
+          pb1[nt][e & 1] += dpre;
+          acc[nt][e] = dpre;
+        }
+        uint32_t h0, l0, h1, l1;
+        split_pair(acc[nt][0], acc[nt][1], h0, l0);  // row g
+        split_pair(acc[nt][2], acc[nt][3], h1, l1);  // row g + 8
+        const int col = 8 * nt + 2 * t;
+        *reinterpret_cast<uint32_t*>(dp_hi + (16 * mt + g) * TS + col) = h0;
+        *reinterpret_cast<uint32_t*>(dp_lo + (16 * mt + g) * TS + col) = l0;
+        *reinterpret_cast<uint32_t*>(dp_hi + (16 * mt + g + 8) * TS + col) = h1;
+        *reinterpret_cast<uint32_t*>(dp_lo + (16 * mt + g + 8) * TS + col) = l1;
+        // accumulator fragment -> A fragment of the dEnc product (k-tile nt/2, halves by nt parity)
+        da_hi[nt / 2][2 * (nt & 1) + 0] = h0; da_hi[nt / 2][2 * (nt & 1) + 1] = h1;
+        da_lo[nt / 2][2 * (nt & 1) + 0] = l0; da_lo[nt / 2][2 * (nt & 1) + 1] = l1;
+      }
+      // dEnc (16 x K0) = dPre1 (16 x H) . W1 (H x K0); B[k = j][n = kenc] = W1^T planes [kenc][j]
+#pragma unroll
+      for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
+        float dacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int kt2 = 0; kt2 < H / 16; ++kt2) {
+          const int off = (8 * nt2 + g) * TS + 16 * kt2 + 2 * t;
+          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wt_hi + off), bh1 = *reinterpret_cast<const uint32_t*>(wt_hi + off + 8);
+          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wt_lo + off), bl1 = *reinterpret_cast<const uint32_t*>(wt_lo + off + 8);
+          mma_bf16_16816(dacc, da_lo[kt2], bh0, bh1);
+          mma_bf16_16816(dacc, da_hi[kt2], bl0, bl1);
+          mma_bf16_16816(dacc, da_hi[kt2], bh0, bh1);
+        }
+        // fused scatter: this lane holds dEnc of level 4*nt2 + t, its pair partner (t ^ 1) the neighbouring level
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pv[e] = __shfl_xor_sync(0xffffffffu, dacc[e], 1);
+        const int b0 = t & 1;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {  // 0: the pair's even level, 1: its odd level
+          const int level = 4 * nt2 + (t & ~1) + which;
+          const bool mine = (which == b0);
+          const LevelDev lv = lvs[level];
+          float* tbl = grad_tables + lv.offset;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {  // rows g and g + 8 of the m-tile
+            const bool live = (rr == 0 ? r_lo : r_hi) < n;
+            Feat<2> gfeat;
+            gfeat.v[0] = mine ? dacc[2 * rr] : pv[2 * rr];
+            gfeat.v[1] = mine ? dacc[2 * rr + 1] : pv[2 * rr + 1];
+            const Cell<D> cell = make_cell<D>(rr == 0 ? xv_lo : xv_hi, lv);
+            if (nt2 < MERGE_NT2) {
+              // coarse levels of a locality-ordered batch: duplicates along the axis-0 line are summed in registers
+              const float w0 = b0 ? cell.wu[0] : cell.wl[0];
+              const MergedHalf mh = merge_line_runs(cell.lo[0] + static_cast<uint32_t>(b0), gfeat.v[0] * w0, gfeat.v[1] * w0,
+                                                    live, line_mask[rr], lane);
+              if (mh.active) {
+                if (lv.is_pow2) scatter_half_level_merged<D, true>(cell, b0, lv, tbl, mh.v0, mh.v1);
+                else scatter_half_level_merged<D, false>(cell, b0, lv, tbl, mh.v0, mh.v1);
+              }
+            } else if (live) {
+              if (lv.is_pow2) scatter_half_level<D, 2, true>(cell, b0, lv, tbl, gfeat);
+              else scatter_half_level<D, 2, false>(cell, b0, lv, tbl, gfeat);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // dW1 (H x K0) += dPre1^T (H x 32) . enc (32 x K0), operands transposed on the way out of shared memory
+    const int lm = lane >> 3, lr = lane & 7;
+#pragma unroll
+    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
+      uint32_t bh[4], bl[4];  // {b0,b1} of coordinate k-tile 0, {b0,b1} of k-tile 1
+      ldmatrix_x4_trans(bh, e_hi + (8 * lm + lr) * WS + 8 * nt2);
+      ldmatrix_x4_trans(bl, e_lo + (8 * lm + lr) * WS + 8 * nt2);
+#pragma unroll
+      for (int jt = 0; jt < H / 16; ++jt) {
+#pragma unroll
+        for (int ct = 0; ct < 2; ++ct) {
+          uint32_t ah[4], al[4];
+          const int off = (16 * ct + 8 * (lm >> 1) + lr) * TS + 16 * jt + 8 * (lm & 1);
+          ldmatrix_x4_trans(ah, dp_hi + off);
+          ldmatrix_x4_trans(al, dp_lo + off);
+          mma_bf16_16816(wacc[jt][nt2], al, bh[2 * ct], bh[2 * ct + 1]);
+          mma_bf16_16816(wacc[jt][nt2], ah, bl[2 * ct], bl[2 * ct + 1]);
+          mma_bf16_16816(wacc[jt][nt2], ah, bh[2 * ct], bh[2 * ct + 1]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- flush ----
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(warp_base);  // reuse the per-warp staging area: [NWARP][H*K0] floats
+  static_assert(sizeof(float) * H * K0 <= 2 * 32 * ((H + MMA_PAD) + (K0 + MMA_PAD)) * sizeof(__nv_bfloat16), "staging too small");
+  float* mine = reinterpret_cast<float*>(dp_hi);
+#pragma unroll
+  for (int jt = 0; jt < H / 16; ++jt)
+#pragma unroll
+    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
+      const int j = 16 * jt + g, k = 8 * nt2 + 2 * t;
+      mine[j * K0 + k] = wacc[jt][nt2][0];
+      mine[j * K0 + k + 1] = wacc[jt][nt2][1];
+      mine[(j + 8) * K0 + k] = wacc[jt][nt2][2];
+      mine[(j + 8) * K0 + k + 1] = wacc[jt][nt2][3];
+    }
+  __syncthreads();
+  constexpr int WARP_STRIDE_F = 2 * 32 * (TS + WS) * static_cast<int>(sizeof(__nv_bfloat16)) / static_cast<int>(sizeof(float));
+  for (int e = threadIdx.x; e < H * K0; e += DEC_THREADS) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NWARP; ++w) s += red[w * WARP_STRIDE_F + e];
+    red_add_f32(gw1 + e, s);
+  }
+  // column partials: sum over the 8 row groups (lanes with equal t), then one atomic per warp and column
+#pragma unroll
+  for (int nt = 0; nt < H / 8; ++nt)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float vb = pb1[nt][q], vw = pw2[nt][q];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        vb += __shfl_xor_sync(0xffffffffu, vb, o);
+        vw += __shfl_xor_sync(0xffffffffu, vw, o);
+      }
+      if (g == 0) {
+        red_add_f32(gb1 + 8 * nt + 2 * t + q, vb);
+        red_add_f32(gw2 + 8 * nt + 2 * t + q, vw);
+      }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pb2 += __shfl_xor_sync(0xffffffffu, pb2, o);
+  if (lane == 0) red_add_f32(gb2, pb2);
+}
+
+template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
+int launch_fused_bwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* pre2,
+                     const float* gy, int act2, const float* x, const LevelTable& T, float* grad_tables, float* gw1, float* gb1,
+                     float* gw2, float* gb2, cudaStream_t s) {
+  constexpr size_t smem = mma_bwd_smem_bytes<K0, H>();
+  static DeviceCache attr_set;
+  const int dev = DeviceCache::device();
+  if (!attr_set.slot[dev].load(std::memory_order_acquire)) {
+    MRI_CUDA_OK(cudaFuncSetAttribute(hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+    attr_set.slot[dev].store(1, std::memory_order_release);
+  }
+  int64_t blocks = ((n + 31) / 32 + 3) / 4;
+  const int64_t cap = 2LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS><<<static_cast<int>(blocks), DEC_THREADS, smem, s>>>(
+      enc, n, w1, b1, w2, pre2, gy, act2, x, T, grad_tables, gw1, gb1, gw2, gb2);
+  MRI_LAUNCH_OK("hashdecoder_mma_bwd_kernel");
+  return MRI_OK;
+}
+
+}  // namespace
+}  // namespace mri
+
+using namespace mri;
+
+extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, const float* enc, int k0, int h, const float* w1,
+                                        const float* b1, const float* w2, const float* pre2, const float* grad_y, int act1, int act2,
+                                        float* grad_tables, const mri_level_t* host_levels, int n_levels, int n_features,
+                                        float* grad_w1, float* grad_b1, float* grad_w2, float* grad_b2, void* stream) {
+  if (n < 0) return fail(MRI_ERR_INVALID, "hashdecoder_backward: negative n");
+  if (n == 0) return MRI_OK;
+  if (!x || !enc || !w1 || !b1 || !w2 || !pre2 || !grad_y || !grad_tables || !host_levels || !grad_w1 || !grad_b1 || !grad_w2 || !grad_b2)
+    return fail(MRI_ERR_INVALID, "hashdecoder_backward: null pointer");
+  if (n_features != 2 || k0 != 2 * n_levels || k0 != 32 || h != 64 || (act1 != MRI_ACT_GELU && act1 != MRI_ACT_RELU) || dim < 3 || dim > 4)
+    return fail(MRI_ERR_UNSUPPORTED, "hashdecoder_backward: fused kernel covers F=2, L=16, H=64, dim 3/4, GELU/ReLU "
+                                     "(got F=%d L=%d H=%d dim=%d act=%d)", n_features, n_levels, h, dim, act1);
+  const uintptr_t need = dim == 4 ? 15 : 3;
+  if ((reinterpret_cast<uintptr_t>(x) & need) || (reinterpret_cast<uintptr_t>(grad_tables) & 15) || (reinterpret_cast<uintptr_t>(enc) & 15))
+    return fail(MRI_ERR_INVALID, "hashdecoder_backward: misaligned pointer");
+  for (int l = 0; l < n_levels; ++l)
+    if (host_levels[l].offset % 2) return fail(MRI_ERR_INVALID, "hashdecoder_backward: level %d offset not aligned", l);
+  LevelTable T;
+  int st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // MRI_BWD_MERGE_LEVELS=0 switches the merging of axis-0 duplicates on the 8 coarsest levels off (A/B runs)
+  static const int merge_nt2 = [] {
+    const char* e = getenv("MRI_BWD_MERGE_LEVELS");
+    return (e && atoi(e) == 0) ? 0 : 2;
+  }();
+  static const bool contiguous = [] { const char* e = getenv("MRI_BWD_CONTIGUOUS"); return !e || atoi(e) != 0; }();
+#define CALL(DV, ACTV, MV, CV) launch_fused_bwd<DV, 32, 64, ACTV, MV, CV>(enc, n, w1, b1, w2, pre2, grad_y, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2, grad_b2, s)
+#define CALL_M(DV, ACTV) (merge_nt2 == 0 ? (contiguous ? CALL(DV, ACTV, 0, true) : CALL(DV, ACTV, 0, false)) \
+                                         : (contiguous ? CALL(DV, ACTV, 2, true) : CALL(DV, ACTV, 2, false)))
+  if (dim == 4 && act1 == MRI_ACT_GELU) return CALL_M(4, MRI_ACT_GELU);
+  if (dim == 4 && act1 == MRI_ACT_RELU) return CALL_M(4, MRI_ACT_RELU);
+  if (dim == 3 && act1 == MRI_ACT_GELU) return CALL_M(3, MRI_ACT_GELU);
+  return CALL_M(3, MRI_ACT_RELU);
+#undef CALL_M
+#undef CALL
+}
+
+extern "C" int mri_hashdecoder_supported(int dim, int n_levels, int n_features, int h, int act1) {
+  return (n_features == 2 && n_levels == 16 && h == 64 && (dim == 3 || dim == 4) && (act1 == MRI_ACT_GELU || act1 == MRI_ACT_RELU)) ? 1 : 0;
+}

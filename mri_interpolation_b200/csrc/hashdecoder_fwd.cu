@@ -139,11 +139,16 @@ template <int D, int ACT1, class Coords>
 int launch_fused_fwd(const Coords& src, int64_t n, const float* tables, const LevelTable& T, const float* w1, const float* b1,
                      const float* w2, const float* b2, int act2, float* enc, float* y, float* pre2, cudaStream_t s) {
   auto kernel = hashdecoder_mma_fwd_kernel<D, 32, 64, ACT1, Coords>;
-  static int resident = 0;  // persistent grid = exactly one wave (blocks walk the tiles with a grid stride): a cap that
-  if (resident == 0) {      // is not a multiple of the resident block count costs a whole extra pass of the tail blocks
+  // persistent grid = exactly one wave (blocks walk the tiles with a grid stride): a cap that is not a multiple of
+  // the resident block count costs a whole extra pass of the tail blocks.  Cached per device.
+  static DeviceCache resident_cache;
+  const int dev = DeviceCache::device();
+  int resident = resident_cache.slot[dev].load(std::memory_order_acquire);
+  if (resident == 0) {
     int per_sm = 0;
     MRI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DEC_THREADS, 0));
     resident = (per_sm > 0 ? per_sm : 1) * sm_count();
+    resident_cache.slot[dev].store(resident, std::memory_order_release);
   }
   int64_t blocks = ((n + 15) / 16 + 3) / 4;
   if (blocks > resident) blocks = resident;

@@ -78,4 +78,32 @@ __device__ __forceinline__ void hidden_mma(const uint32_t (&a_hi)[K0 / 16][4], c
   }
 }
 
+template <int ACT>
+__device__ __forceinline__ void act_and_grad(float pre, float& a, float& g) {
+  if constexpr (ACT == MRI_ACT_GELU) {
+    float cdf, pdf;
+    gelu_cdf_pdf(pre, cdf, pdf);
+    a = pre * cdf;
+    g = cdf + pre * pdf;
+  } else if constexpr (ACT == MRI_ACT_RELU) {
+    a = fmaxf(pre, 0.0f);
+    g = pre > 0.0f ? 1.0f : 0.0f;
+  } else {
+    a = pre;
+    g = 1.0f;
+  }
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <int K0, int H>
+constexpr size_t mma_bwd_smem_bytes() {
+  return 2 * (H * (K0 + MMA_PAD) + K0 * (H + MMA_PAD)) * sizeof(__nv_bfloat16) + 2 * H * sizeof(float) +
+         (DEC_THREADS / 32) * 2 * 32 * ((H + MMA_PAD) + (K0 + MMA_PAD)) * sizeof(__nv_bfloat16);
+}
+
 }  // namespace mri

@@ -354,6 +354,39 @@ def grid_coords(axes: Sequence[torch.Tensor], first: int, count: int, device) ->
     return out
 
 
+def locality_key(index: torch.Tensor, shape: Sequence[int], block: int = 4) -> torch.Tensor:
+    """Sort key that puts voxels sharing hash-table sectors next to each other in a batch.
+
+    Axis 0 is the only axis whose hash prime is 1 (encoding.py:40), so at every level the rows of cells that are
+    neighbours along axis 0 differ in their low bits only - they share 32-byte sectors / 128-byte lines - while a step
+    along any other axis lands on an unrelated row.  The key therefore walks axis 0 fastest inside strips of ``block``
+    axis-1 voxels (coarse levels also share cells across a few axis-1 neighbours), the remaining axes slowest.  The
+    loss is a mean over the batch: the order of a batch changes nothing but the memory access pattern."""
+    shape = [int(s) for s in shape]
+    rem = index
+    v = []
+    for s in reversed(shape):
+        v.append(rem % s)
+        rem = rem // s
+    v = v[::-1]  # per-axis voxel indices, axis 0 first
+    if len(shape) == 1:
+        return v[0]
+    key = torch.zeros_like(index)
+    for d in range(len(shape) - 1, 1, -1):
+        key = key * shape[d] + v[d]
+    if block > 1:
+        key = ((key * ((shape[1] + block - 1) // block) + v[1] // block) * shape[0] + v[0]) * block + v[1] % block
+    else:
+        key = (key * shape[1] + v[1]) * shape[0] + v[0]
+    return key
+
+
+def locality_sort(index: torch.Tensor, shape: Sequence[int], block: int = 4) -> torch.Tensor:
+    """``index`` (..., n) voxel indices -> same sets, each row ordered by `locality_key`."""
+    order = torch.argsort(locality_key(index, shape, block), dim=-1)
+    return torch.gather(index, -1, order)
+
+
 class VoxelSampler:
     """Device-resident volume -> training batches from voxel indices (coordinates synthesised in-kernel)."""
 

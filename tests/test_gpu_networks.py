@@ -318,6 +318,58 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(geo):
                 assert rel_err(pf.grad, ref) < 1e-3, (n, name)
 
 
+@pytest.mark.parametrize("geo", [FUSED_GEOMETRIES[1], FUSED_GEOMETRIES[2]])
+@pytest.mark.parametrize("order", ["line", "line_descending", "dense_duplicates"])
+def test_fused_backward_merges_axis0_runs_of_locality_ordered_batches(geo, order):
+    """Batches ordered along axis 0 (functional.locality_sort) put samples of one axis-0 line in consecutive rows; the
+    fused backward sums their coinciding corner updates in registers before the reduction (hash_device.cuh
+    merge_line_runs).  Grid voxels of a small volume, dense enough that runs of equal / adjacent cells, line changes
+    inside a tile, repeated voxels and a ragged tail all occur; gradients must equal the oracle's and be independent of
+    the order of the batch."""
+    import copy
+    from mri_interpolation_b200 import functional as Fn, models
+    from oracle import networks
+    dim = geo["dim_in"]
+    shape = (37, 5, 3, 2)[:dim]
+    kw = dict(n_levels=16, n_features_per_level=2, dim_hidden=64, dim_out=1, n_layers=2, **geo)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False)
+    gen = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
+    params = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items() if not k.startswith("layers.")}
+    levels = networks.hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
+    total = int(np.prod(shape))
+    if order == "dense_duplicates":
+        index = torch.randint(0, total, (3 * total + 5,), generator=gen)  # every voxel ~3 times: equal cells at every level
+    else:
+        index = torch.randperm(total, generator=gen)[: total - 7]
+    index = Fn.locality_sort(index, shape, block=1)
+    if order == "line_descending":
+        index = index.flip(0)
+    axes = [torch.linspace(0, 1, s) for s in shape]
+    rem, cols = index.clone(), []
+    for d in range(dim - 1, -1, -1):
+        cols.append(axes[d][rem % shape[d]])
+        rem = rem // shape[d]
+    x = torch.stack(cols[::-1], dim=-1).contiguous()
+    y = torch.rand(x.shape[0], 1, generator=gen)
+    F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, False)).backward()
+    fused = copy.deepcopy(net).to(DEV)
+    assert type(fused(x.to(DEV)).grad_fn).__name__.startswith("HashDecoderFn")
+    fused.training_step((x.to(DEV), y.to(DEV)), 0).backward()
+    shuffled = copy.deepcopy(net).to(DEV)
+    perm = torch.randperm(x.shape[0], generator=gen)
+    shuffled.training_step((x[perm].to(DEV), y[perm].to(DEV)), 0).backward()
+    for (name, pf), (_, ps) in zip(fused.named_parameters(), shuffled.named_parameters()):
+        if name.startswith("layers."):
+            continue
+        ref = params[name].grad
+        assert rel_err(pf.grad, ref) < 1e-3, name
+        assert rel_err(pf.grad, ps.grad) < 1e-4, name
+
+
 @pytest.mark.parametrize("geo,act", [(FUSED_GEOMETRIES[0], "gelu"), (FUSED_GEOMETRIES[1], "relu"), (FUSED_GEOMETRIES[2], "relu"),
                                      (FUSED_GEOMETRIES[3], "gelu")])
 def test_fused_hashdecoder_forward_matches_two_kernel_path_and_oracle(geo, act):
