@@ -224,6 +224,8 @@ def workload_config(args, cpu_sample=None):
                                                  if args.gpus > 1 else ""), "l2": "inputs larger than L2: every step streams the whole p/g/m/v arena through Adam "
                                                   "(hash: 489 MB/step) plus per-batch activations (SIREN: > 1 GB/layer)"}
     cfg["allocator_priming_steps_before_warmup"] = PRIMING_STEPS
+    cfg["batch_order"] = os.environ.get("MRI_BATCH_ORDER", "axis0") + (": i.i.d. uniform voxel indices, each batch arranged with the "
+                                                                        "axis-0 index fastest (same sets; the loss is order-invariant)")
     if cpu_sample:
         cfg["cpu_sample_coords_per_step"] = cpu_sample
     return cfg
@@ -316,10 +318,22 @@ def main():
     # the shuffled index stream is drawn up front (like a DataLoader sampler), as a ring of 32 batches
     ring = 32
     index = torch.randint(0, sampler.total, (ring, n), device=dev, generator=gen)
-    batch_order = os.environ.get("MRI_BATCH_ORDER", "blk4")
+    # locality-ordered batches (the loaders' default, datamodules.DeviceBatchLoader / functional.locality_sort): the SAME
+    # random voxel sets, arranged inside a batch with the axis-0 index fastest.  MRI_BATCH_ORDER=none keeps the drawn order.
+    from mri_interpolation_b200 import functional as Fn
+    batch_order = os.environ.get("MRI_BATCH_ORDER", "axis0")
     if batch_order != "none":
-        from mri_interpolation_b200 import functional as Fn
         index = Fn.locality_sort(index, info["shape"], block=int(batch_order[3:]) if batch_order.startswith("blk") else 1)
+    # what drawing + ordering one batch costs on the device (index generation is loader work outside the timed step;
+    # DeviceBatchLoader amortises it into one stable sort per epoch)
+    torch.cuda.synchronize()
+    _t0 = time.perf_counter()
+    for _ in range(8):
+        _i = torch.randint(0, sampler.total, (n,), device=dev, generator=gen)
+        if batch_order != "none":
+            _i = Fn.locality_sort(_i, info["shape"], block=1)
+    torch.cuda.synchronize()
+    sampler_ms = (time.perf_counter() - _t0) / 8 * 1e3
 
     def step(i):
         x, y = sampler.batch(index[i % ring])
@@ -586,7 +600,7 @@ def main():
             "data": info["data"], "config": workload_config(args), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": n * (dim + 1) * 4, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
-            "gpu_launches": launches, "final_loss": final_loss,
+            "gpu_launches": launches, "final_loss": final_loss, "sampler_ms_per_batch": sampler_ms,
             "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "infer": infer,
         }
         print(json.dumps(line))

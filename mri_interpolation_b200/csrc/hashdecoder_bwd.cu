@@ -11,12 +11,31 @@
 namespace mri {
 namespace {
 
-// Same kernel with the table scatter fused in: the dEnc accumulator fragments (rows g / g+8, level 4*nt2 + t for
-// F = 2) never go to memory - lane pairs (t even / odd) exchange their two levels with one shuffle and then act as the
-// lower / upper axis-0 halves of the pair-lane scatter (hash_device.cuh), so the red.global.add traffic overlaps the
-// tensor-core and GELU work of the next tile.
+constexpr int BWD_WARPS = 6;               // 192 threads, 2 blocks per SM (168 registers): 12 warps per SM
+constexpr int BWD_THREADS = 32 * BWD_WARPS;
+
+template <int K0, int H>
+constexpr size_t fused_bwd_smem_bytes() {
+  return 2 * (H * (K0 + MMA_PAD) + K0 * (H + MMA_PAD)) * sizeof(__nv_bfloat16)  // W1 and W1^T planes
+         + 2 * H * sizeof(float)                                               // b1, w2
+         + BWD_WARPS * (2 * 16 * ((H + MMA_PAD) + (K0 + MMA_PAD)) * sizeof(__nv_bfloat16)  // per-warp dPre1 / enc planes of one m-tile
+                        + H * K0 * sizeof(float));                                          // per-warp dW1 accumulator
+}
+
+// Decoder backward on the tensor cores with the table scatter fused in.  Per warp and per 16-coordinate m-tile:
+//   (1) recompute pre1 = enc W1^T + b1 (mma.sync, as in the forward), form dPre1 = dPre2 w2 act1'(pre1) on the fragments
+//   (2) dEnc = dPre1 W1: the accumulator fragments ARE the A fragments of the next mma (no data movement); all four
+//       8-column blocks are issued back to back (four independent accumulator chains)
+//   (3) dW1 += dPre1^T enc: both operands go through warp-private shared memory and come back transposed with
+//       ldmatrix.trans; the 64 x 32 fp32 accumulator lives in warp-private shared memory in fragment order and passes
+//       through registers only here - keeping it in registers for the whole loop (round 1) cost 64 of 253 registers and
+//       held the kernel at 8 warps per SM, where ncu showed it latency-bound (issue slots 26-32 % busy)
+//   (4) scatter: the dEnc fragments (rows g / g+8, level 4*nt2 + t for F = 2) never go to memory - lane pairs (t even /
+//       odd) exchange their two levels with one shuffle and act as the lower / upper axis-0 halves of the pair-lane
+//       scatter (hash_device.cuh); on the coarse levels duplicates along an axis-0 line are merged first.
+// db1 / dw2 / db2 are per-thread column partials reduced once at the end.
 template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
-__global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(const float* __restrict__ enc, int64_t n,
+__global__ void __launch_bounds__(BWD_THREADS, 2) hashdecoder_mma_bwd_kernel(const float* __restrict__ enc, int64_t n,
                                                                            const float* __restrict__ w1, const float* __restrict__ b1,
                                                                            const float* __restrict__ w2, const float* __restrict__ pre2,
                                                                            const float* __restrict__ gy, int act2,
@@ -24,9 +43,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
                                                                            float* __restrict__ grad_tables, float* __restrict__ gw1,
                                                                            float* __restrict__ gb1, float* __restrict__ gw2,
                                                                            float* __restrict__ gb2) {
+  static_assert(K0 == 32 && H % 16 == 0, "F = 2, L = 16");
   constexpr int WS = K0 + MMA_PAD;   // row stride of W1 / enc planes (bf16 elements)
   constexpr int TS = H + MMA_PAD;    // row stride of W1^T / dPre1 planes
-  constexpr int NWARP = DEC_THREADS / 32;
+  constexpr int STAGE = 2 * 16 * (TS + WS);  // bf16 elements of one warp's staging area
   extern __shared__ __align__(16) uint8_t msm[];
   __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(msm);   // [H][WS]
   __nv_bfloat16* w_lo = w_hi + H * WS;
@@ -34,40 +54,36 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
   __nv_bfloat16* wt_lo = wt_hi + K0 * TS;
   float* b1s = reinterpret_cast<float*>(wt_lo + K0 * TS);
   float* w2s = b1s + H;
-  __nv_bfloat16* warp_base = reinterpret_cast<__nv_bfloat16*>(w2s + H);
+  float* wacc_all = w2s + H;                                      // [BWD_WARPS][H/16][K0/8][32 lanes][4]
+  __nv_bfloat16* stage_all = reinterpret_cast<__nv_bfloat16*>(wacc_all + BWD_WARPS * H * K0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
-  __nv_bfloat16* dp_hi = warp_base + warp * (2 * 32 * (TS + WS));  // [32][TS]
-  __nv_bfloat16* dp_lo = dp_hi + 32 * TS;
-  __nv_bfloat16* e_hi = dp_lo + 32 * TS;                            // [32][WS]
-  __nv_bfloat16* e_lo = e_hi + 32 * WS;
+  float4* wacc_s = reinterpret_cast<float4*>(wacc_all + warp * H * K0) + lane;   // + 32 * (jt * K0/8 + nt2)
+  __nv_bfloat16* dp_hi = stage_all + warp * STAGE;                 // [16][TS]
+  __nv_bfloat16* dp_lo = dp_hi + 16 * TS;
+  __nv_bfloat16* e_hi = dp_lo + 16 * TS;                           // [16][WS]
+  __nv_bfloat16* e_lo = e_hi + 16 * WS;
 
   stage_planes<H, K0>(w1, w_hi, w_lo, false);
   stage_planes<H, K0>(w1, wt_hi, wt_lo, true);
-  for (int e = threadIdx.x; e < H; e += DEC_THREADS) {
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
     b1s[e] = __ldg(b1 + e);
     w2s[e] = __ldg(w2 + e);
   }
+  for (int e = threadIdx.x; e < BWD_WARPS * H * K0; e += blockDim.x) wacc_all[e] = 0.0f;
   // the lanes of one instruction work on two different levels: a lane-indexed read of the __grid_constant__ table is a
   // replayed LDC on the long scoreboard (17 % of the stall samples in ncu) - shared memory serves it in one pass
   __shared__ LevelDev lvs[K0 / 2];
   if (threadIdx.x < K0 / 2) lvs[threadIdx.x] = T.lv[threadIdx.x];
   __syncthreads();
 
-  float wacc[H / 16][K0 / 8][4];
-#pragma unroll
-  for (int a = 0; a < H / 16; ++a)
-#pragma unroll
-    for (int b = 0; b < K0 / 8; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) wacc[a][b][c] = 0.0f;
   float pb1[H / 8][2], pw2[H / 8][2];
 #pragma unroll
   for (int nt = 0; nt < H / 8; ++nt) { pb1[nt][0] = pb1[nt][1] = 0.0f; pw2[nt][0] = pw2[nt][1] = 0.0f; }
   float pb2 = 0.0f;
 
   // inputs of one 16-row m-tile as they come out of global memory; the next tile's are requested before the current
-  // tile is processed (2 warps per scheduler cannot hide a DRAM round trip per tile on their own)
+  // tile is processed
   struct TileIn {
     float2 e[K0 / 16][2][2];  // [k-tile][8-column half][row g / g+8]
     float gy[2], p2[2];
@@ -90,69 +106,70 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
     }
   };
 
-  // Every warp walks its OWN contiguous range of 32-row chunks.  With a locality-ordered batch a grid-stride walk would
-  // make all resident warps work on neighbouring samples at the same time, i.e. reduce into the same few rows of the
-  // coarse levels at once - and the L2 serialises reductions on one address (measured: 2.2x slower when 8192 rows are
-  // hot grid-wide).  Warps that are far apart in the batch are far apart in the volume.
-  const int64_t chunks = (n + 31) / 32;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * NWARP;
-  const int64_t wid = static_cast<int64_t>(blockIdx.x) * NWARP + warp;
-  const int64_t chunk_end = CONTIGUOUS ? ((wid + 1) * chunks) / n_warps : chunks;
-  const int64_t chunk_stride = CONTIGUOUS ? 1 : n_warps;
-  int64_t chunk = CONTIGUOUS ? (wid * chunks) / n_warps : wid;
+  // Every warp walks its OWN contiguous range of m-tiles.  With a locality-ordered batch a grid-stride walk would make
+  // all resident warps work on neighbouring samples at the same time, i.e. reduce into the same few rows of the coarse
+  // levels at once - and the L2 serialises reductions on one address (measured: 2.2x slower when 8192 rows are hot
+  // grid-wide).  Warps that are far apart in the batch are far apart in the volume.
+  const int64_t tiles = (n + 15) / 16;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * BWD_WARPS;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * BWD_WARPS + warp;
+  const int64_t tile_end = CONTIGUOUS ? ((wid + 1) * tiles) / n_warps : tiles;
+  const int64_t tile_stride = CONTIGUOUS ? 1 : n_warps;
+  int64_t tile = CONTIGUOUS ? (wid * tiles) / n_warps : wid;
   TileIn nxt;
-  fetch(chunk * 32, nxt);
-  for (; chunk < chunk_end; chunk += chunk_stride) {
+  fetch(tile * 16, nxt);
 #pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
-      const int64_t row0 = chunk * 32 + 16 * mt;
-      const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
-      const TileIn cur = nxt;
-      fetch(mt == 0 ? row0 + 16 : (chunk + chunk_stride) * 32, nxt);
-      float xv_lo[D], xv_hi[D];
+  for (; tile < tile_end; tile += tile_stride) {
+    const int64_t row0 = tile * 16;
+    const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
+    const TileIn cur = nxt;
+    fetch((tile + tile_stride) * 16, nxt);
+    float xv_lo[D], xv_hi[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) { xv_lo[d] = cur.xv[0][d]; xv_hi[d] = cur.xv[1][d]; }
-      // rows g, g+1 of an 8-row group live and on one axis-0 line (identical coordinates on every other axis)
-      uint32_t line_mask[2] = {0u, 0u};
-      if constexpr (MERGE_NT2 > 0) {
+    for (int d = 0; d < D; ++d) { xv_lo[d] = cur.xv[0][d]; xv_hi[d] = cur.xv[1][d]; }
+    // rows g, g+1 of an 8-row group live and on one axis-0 line (identical coordinates on every other axis)
+    uint32_t line_mask[2] = {0u, 0u};
+    if constexpr (MERGE_NT2 > 0) {
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          bool same = g < 7 && (rr == 0 ? r_lo : r_hi) + 1 < n;
+      for (int rr = 0; rr < 2; ++rr) {
+        bool same = g < 7 && (rr == 0 ? r_lo : r_hi) + 1 < n;
 #pragma unroll
-          for (int d = 1; d < D; ++d) {
-            const float mine = rr == 0 ? xv_lo[d] : xv_hi[d];
-            const float next = __shfl_down_sync(0xffffffffu, mine, 4);  // every lane takes part: no short-circuit around it
-            same = same && next == mine;
-          }
-          line_mask[rr] = __ballot_sync(0xffffffffu, same);
+        for (int d = 1; d < D; ++d) {
+          const float mine = rr == 0 ? xv_lo[d] : xv_hi[d];
+          const float next = __shfl_down_sync(0xffffffffu, mine, 4);  // every lane takes part: no short-circuit around it
+          same = same && next == mine;
         }
+        line_mask[rr] = __ballot_sync(0xffffffffu, same);
       }
-      float acc[H / 8][4];
-      {
-        uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
+    }
+    float acc[H / 8][4];
+    {
+      uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
 #pragma unroll
-        for (int kt = 0; kt < K0 / 16; ++kt)
+      for (int kt = 0; kt < K0 / 16; ++kt)
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
-            split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
-          }
+        for (int half = 0; half < 2; ++half) {
+          split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
+          split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+        }
 #pragma unroll
-        for (int kt = 0; kt < K0 / 16; ++kt)
+      for (int kt = 0; kt < K0 / 16; ++kt)
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int col = 16 * kt + 8 * half + 2 * t;
-            *reinterpret_cast<uint32_t*>(e_hi + (16 * mt + g) * WS + col) = a_hi[kt][2 * half];
-            *reinterpret_cast<uint32_t*>(e_lo + (16 * mt + g) * WS + col) = a_lo[kt][2 * half];
-            *reinterpret_cast<uint32_t*>(e_hi + (16 * mt + g + 8) * WS + col) = a_hi[kt][2 * half + 1];
-            *reinterpret_cast<uint32_t*>(e_lo + (16 * mt + g + 8) * WS + col) = a_lo[kt][2 * half + 1];
-          }
-        hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
-      }
-      float dp2_lo = 0.0f, dp2_hi = 0.0f;
-      if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
-      if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
-      if (t == 0) pb2 += dp2_lo + dp2_hi;
+        for (int half = 0; half < 2; ++half) {
+          const int col = 16 * kt + 8 * half + 2 * t;
+          *reinterpret_cast<uint32_t*>(e_hi + g * WS + col) = a_hi[kt][2 * half];
+          *reinterpret_cast<uint32_t*>(e_lo + g * WS + col) = a_lo[kt][2 * half];
+          *reinterpret_cast<uint32_t*>(e_hi + (g + 8) * WS + col) = a_hi[kt][2 * half + 1];
+          *reinterpret_cast<uint32_t*>(e_lo + (g + 8) * WS + col) = a_lo[kt][2 * half + 1];
+        }
+      hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
+    }
+    float dp2_lo = 0.0f, dp2_hi = 0.0f;
+    if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
+    if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
+    if (t == 0) pb2 += dp2_lo + dp2_hi;
+    float dacc[K0 / 8][4];
+    {
       uint32_t da_hi[H / 16][4], da_lo[H / 16][4];
 #pragma unroll
       for (int nt = 0; nt < H / 8; ++nt) {
@@ -170,10 +187,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
         split_pair(acc[nt][0], acc[nt][1], h0, l0);  // row g
         split_pair(acc[nt][2], acc[nt][3], h1, l1);  // row g + 8
         const int col = 8 * nt + 2 * t;
-        *reinterpret_cast<uint32_t*>(dp_hi + (16 * mt + g) * TS + col) = h0;
-        *reinterpret_cast<uint32_t*>(dp_lo + (16 * mt + g) * TS + col) = l0;
-        *reinterpret_cast<uint32_t*>(dp_hi + (16 * mt + g + 8) * TS + col) = h1;
-        *reinterpret_cast<uint32_t*>(dp_lo + (16 * mt + g + 8) * TS + col) = l1;
+        *reinterpret_cast<uint32_t*>(dp_hi + g * TS + col) = h0;
+        *reinterpret_cast<uint32_t*>(dp_lo + g * TS + col) = l0;
+        *reinterpret_cast<uint32_t*>(dp_hi + (g + 8) * TS + col) = h1;
+        *reinterpret_cast<uint32_t*>(dp_lo + (g + 8) * TS + col) = l1;
         // accumulator fragment -> A fragment of the dEnc product (k-tile nt/2, halves by nt parity)
         da_hi[nt / 2][2 * (nt & 1) + 0] = h0; da_hi[nt / 2][2 * (nt & 1) + 1] = h1;
         da_lo[nt / 2][2 * (nt & 1) + 0] = l0; da_lo[nt / 2][2 * (nt & 1) + 1] = l1;
@@ -181,98 +198,95 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) hashdecoder_mma_bwd_kernel(con
       // dEnc (16 x K0) = dPre1 (16 x H) . W1 (H x K0); B[k = j][n = kenc] = W1^T planes [kenc][j]
 #pragma unroll
       for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-        float dacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        dacc[nt2][0] = dacc[nt2][1] = dacc[nt2][2] = dacc[nt2][3] = 0.0f;
 #pragma unroll
         for (int kt2 = 0; kt2 < H / 16; ++kt2) {
           const int off = (8 * nt2 + g) * TS + 16 * kt2 + 2 * t;
           const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wt_hi + off), bh1 = *reinterpret_cast<const uint32_t*>(wt_hi + off + 8);
           const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wt_lo + off), bl1 = *reinterpret_cast<const uint32_t*>(wt_lo + off + 8);
-          mma_bf16_16816(dacc, da_lo[kt2], bh0, bh1);
-          mma_bf16_16816(dacc, da_hi[kt2], bl0, bl1);
-          mma_bf16_16816(dacc, da_hi[kt2], bh0, bh1);
-        }
-        // fused scatter: this lane holds dEnc of level 4*nt2 + t, its pair partner (t ^ 1) the neighbouring level
-        float pv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) pv[e] = __shfl_xor_sync(0xffffffffu, dacc[e], 1);
-        const int b0 = t & 1;
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {  // 0: the pair's even level, 1: its odd level
-          const int level = 4 * nt2 + (t & ~1) + which;
-          const bool mine = (which == b0);
-          const LevelDev lv = lvs[level];
-          float* tbl = grad_tables + lv.offset;
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {  // rows g and g + 8 of the m-tile
-            const bool live = (rr == 0 ? r_lo : r_hi) < n;
-            Feat<2> gfeat;
-            gfeat.v[0] = mine ? dacc[2 * rr] : pv[2 * rr];
-            gfeat.v[1] = mine ? dacc[2 * rr + 1] : pv[2 * rr + 1];
-            const Cell<D> cell = make_cell<D>(rr == 0 ? xv_lo : xv_hi, lv);
-            if (nt2 < MERGE_NT2) {
-              // coarse levels of a locality-ordered batch: duplicates along the axis-0 line are summed in registers
-              const float w0 = b0 ? cell.wu[0] : cell.wl[0];
-              const MergedHalf mh = merge_line_runs(cell.lo[0] + static_cast<uint32_t>(b0), gfeat.v[0] * w0, gfeat.v[1] * w0,
-                                                    live, line_mask[rr], lane);
-              if (mh.active) {
-                if (lv.is_pow2) scatter_half_level_merged<D, true>(cell, b0, lv, tbl, mh.v0, mh.v1);
-                else scatter_half_level_merged<D, false>(cell, b0, lv, tbl, mh.v0, mh.v1);
-              }
-            } else if (live) {
-              if (lv.is_pow2) scatter_half_level<D, 2, true>(cell, b0, lv, tbl, gfeat);
-              else scatter_half_level<D, 2, false>(cell, b0, lv, tbl, gfeat);
-            }
-          }
+          mma_bf16_16816(dacc[nt2], da_lo[kt2], bh0, bh1);
+          mma_bf16_16816(dacc[nt2], da_hi[kt2], bl0, bl1);
+          mma_bf16_16816(dacc[nt2], da_hi[kt2], bh0, bh1);
         }
       }
     }
     __syncwarp();
-    // dW1 (H x K0) += dPre1^T (H x 32) . enc (32 x K0), operands transposed on the way out of shared memory
-    const int lm = lane >> 3, lr = lane & 7;
+    // dW1 (H x K0) += dPre1^T (H x 16) . enc (16 x K0), operands transposed on the way out of shared memory
+    {
+      const int lm = lane >> 3, lr = lane & 7;
+      uint32_t bh[K0 / 16][4], bl[K0 / 16][4];  // per pair of 8-column blocks: {b0, b1} of the first, {b0, b1} of the second
 #pragma unroll
-    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-      uint32_t bh[4], bl[4];  // {b0,b1} of coordinate k-tile 0, {b0,b1} of k-tile 1
-      ldmatrix_x4_trans(bh, e_hi + (8 * lm + lr) * WS + 8 * nt2);
-      ldmatrix_x4_trans(bl, e_lo + (8 * lm + lr) * WS + 8 * nt2);
+      for (int np = 0; np < K0 / 16; ++np) {
+        const int off = (8 * (lm & 1) + lr) * WS + 8 * (2 * np + (lm >> 1));
+        ldmatrix_x4_trans(bh[np], e_hi + off);
+        ldmatrix_x4_trans(bl[np], e_lo + off);
+      }
 #pragma unroll
       for (int jt = 0; jt < H / 16; ++jt) {
+        uint32_t ah[4], al[4];
+        const int off = (8 * (lm >> 1) + lr) * TS + 16 * jt + 8 * (lm & 1);
+        ldmatrix_x4_trans(ah, dp_hi + off);
+        ldmatrix_x4_trans(al, dp_lo + off);
 #pragma unroll
-        for (int ct = 0; ct < 2; ++ct) {
-          uint32_t ah[4], al[4];
-          const int off = (16 * ct + 8 * (lm >> 1) + lr) * TS + 16 * jt + 8 * (lm & 1);
-          ldmatrix_x4_trans(ah, dp_hi + off);
-          ldmatrix_x4_trans(al, dp_lo + off);
-          mma_bf16_16816(wacc[jt][nt2], al, bh[2 * ct], bh[2 * ct + 1]);
-          mma_bf16_16816(wacc[jt][nt2], ah, bl[2 * ct], bl[2 * ct + 1]);
-          mma_bf16_16816(wacc[jt][nt2], ah, bh[2 * ct], bh[2 * ct + 1]);
+        for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
+          float4 c4 = wacc_s[32 * (jt * (K0 / 8) + nt2)];
+          float c[4] = {c4.x, c4.y, c4.z, c4.w};
+          const uint32_t h0 = bh[nt2 >> 1][2 * (nt2 & 1)], h1 = bh[nt2 >> 1][2 * (nt2 & 1) + 1];
+          const uint32_t l0 = bl[nt2 >> 1][2 * (nt2 & 1)], l1 = bl[nt2 >> 1][2 * (nt2 & 1) + 1];
+          mma_bf16_16816(c, al, h0, h1);
+          mma_bf16_16816(c, ah, l0, l1);
+          mma_bf16_16816(c, ah, h0, h1);
+          wacc_s[32 * (jt * (K0 / 8) + nt2)] = make_float4(c[0], c[1], c[2], c[3]);
         }
       }
     }
     __syncwarp();
+    // fused scatter: this lane holds dEnc of level 4*nt2 + t, its pair partner (t ^ 1) the neighbouring level.  The
+    // (level of the pair, row of the tile) combinations run as a real loop: fully unrolled the scatter alone was ~60 KB of
+    // SASS and the warps stalled on instruction fetch (ncu: stall_no_instruction 1.3 per issue with 12 warps per SM)
+    const int b0 = t & 1;
+#pragma unroll
+    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
+      float pv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pv[e] = __shfl_xor_sync(0xffffffffu, dacc[nt2][e], 1);
+#pragma unroll 1
+      for (int wr = 0; wr < 4; ++wr) {
+        const int which = wr >> 1, rr = wr & 1;    // which: the pair's even / odd level; rr: rows g / g + 8 of the m-tile
+        const bool mine = (which == b0);
+        const LevelDev lv = lvs[4 * nt2 + (t & ~1) + which];
+        float* tbl = grad_tables + lv.offset;
+        const bool live = (rr ? r_hi : r_lo) < n;
+        const float g0 = mine ? (rr ? dacc[nt2][2] : dacc[nt2][0]) : (rr ? pv[2] : pv[0]);
+        const float g1 = mine ? (rr ? dacc[nt2][3] : dacc[nt2][1]) : (rr ? pv[3] : pv[1]);
+        float xr[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xr[d] = rr ? xv_hi[d] : xv_lo[d];
+        const Cell<D> cell = make_cell<D>(xr, lv);
+        const float w0 = b0 ? cell.wu[0] : cell.wl[0];
+        float v0 = g0 * w0, v1 = g1 * w0;
+        bool active = live;
+        if (nt2 < MERGE_NT2) {
+          // coarse levels of a locality-ordered batch: duplicates along the axis-0 line are summed in registers
+          const MergedHalf mh = merge_line_runs(cell.lo[0] + static_cast<uint32_t>(b0), v0, v1, live, rr ? line_mask[1] : line_mask[0], lane);
+          v0 = mh.v0; v1 = mh.v1; active = mh.active;
+        }
+        if (active) scatter_half_level_weighted<D>(cell, b0, lv, tbl, v0, v1);
+      }
+    }
   }
 
   // ---- flush ----
   __syncthreads();
-  float* red = reinterpret_cast<float*>(warp_base);  // reuse the per-warp staging area: [NWARP][H*K0] floats
-  static_assert(sizeof(float) * H * K0 <= 2 * 32 * ((H + MMA_PAD) + (K0 + MMA_PAD)) * sizeof(__nv_bfloat16), "staging too small");
-  float* mine = reinterpret_cast<float*>(dp_hi);
+  // dW1: sum of the warps' accumulators; element (j, k) sits at fragment position (jt, nt2, lane', c)
+  for (int e = threadIdx.x; e < H * K0; e += blockDim.x) {
+    const int j = e / K0, k = e - j * K0;
+    const int jt = j >> 4, jr = j & 15, nt2 = k >> 3, kc = k & 7;
+    const int idx = ((jt * (K0 / 8) + nt2) * 32 + 4 * (jr & 7) + (kc >> 1)) * 4 + 2 * (jr >> 3) + (kc & 1);
+    float sum = 0.0f;
 #pragma unroll
-  for (int jt = 0; jt < H / 16; ++jt)
-#pragma unroll
-    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-      const int j = 16 * jt + g, k = 8 * nt2 + 2 * t;
-      mine[j * K0 + k] = wacc[jt][nt2][0];
-      mine[j * K0 + k + 1] = wacc[jt][nt2][1];
-      mine[(j + 8) * K0 + k] = wacc[jt][nt2][2];
-      mine[(j + 8) * K0 + k + 1] = wacc[jt][nt2][3];
-    }
-  __syncthreads();
-  constexpr int WARP_STRIDE_F = 2 * 32 * (TS + WS) * static_cast<int>(sizeof(__nv_bfloat16)) / static_cast<int>(sizeof(float));
-  for (int e = threadIdx.x; e < H * K0; e += DEC_THREADS) {
-    float s = 0.0f;
-#pragma unroll
-    for (int w = 0; w < NWARP; ++w) s += red[w * WARP_STRIDE_F + e];
-    red_add_f32(gw1 + e, s);
+    for (int w = 0; w < BWD_WARPS; ++w) sum += wacc_all[w * H * K0 + idx];
+    red_add_f32(gw1 + e, sum);
   }
   // column partials: sum over the 8 row groups (lanes with equal t), then one atomic per warp and column
 #pragma unroll
@@ -299,19 +313,22 @@ template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
 int launch_fused_bwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* pre2,
                      const float* gy, int act2, const float* x, const LevelTable& T, float* grad_tables, float* gw1, float* gb1,
                      float* gw2, float* gb2, cudaStream_t s) {
-  constexpr size_t smem = mma_bwd_smem_bytes<K0, H>();
-  static DeviceCache attr_set;
+  constexpr size_t smem = fused_bwd_smem_bytes<K0, H>();
+  auto kernel = hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS>;
+  static DeviceCache resident_cache;  // resident blocks of this kernel on the current device (one persistent wave)
   const int dev = DeviceCache::device();
-  if (!attr_set.slot[dev].load(std::memory_order_acquire)) {
-    MRI_CUDA_OK(cudaFuncSetAttribute(hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    attr_set.slot[dev].store(1, std::memory_order_release);
+  int resident = resident_cache.slot[dev].load(std::memory_order_acquire);
+  if (resident == 0) {
+    MRI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    MRI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BWD_THREADS, smem));
+    resident = (per_sm > 0 ? per_sm : 1) * sm_count();
+    resident_cache.slot[dev].store(resident, std::memory_order_release);
   }
-  int64_t blocks = ((n + 31) / 32 + 3) / 4;
-  const int64_t cap = 2LL * sm_count();
-  if (blocks > cap) blocks = cap;
-  hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS><<<static_cast<int>(blocks), DEC_THREADS, smem, s>>>(
-      enc, n, w1, b1, w2, pre2, gy, act2, x, T, grad_tables, gw1, gb1, gw2, gb2);
+  int64_t blocks = ((n + 15) / 16 + BWD_WARPS - 1) / BWD_WARPS;
+  if (blocks > resident) blocks = resident;
+  kernel<<<static_cast<int>(blocks), BWD_THREADS, smem, s>>>(enc, n, w1, b1, w2, pre2, gy, act2, x, T, grad_tables, gw1, gb1,
+                                                             gw2, gb2);
   MRI_LAUNCH_OK("hashdecoder_mma_bwd_kernel");
   return MRI_OK;
 }
@@ -341,15 +358,16 @@ extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, cons
   int st = make_level_table(host_levels, n_levels, dim, &T);
   if (st != MRI_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // MRI_BWD_MERGE_LEVELS=0 switches the merging of axis-0 duplicates on the 8 coarsest levels off (A/B runs)
+  // MRI_BWD_MERGE_LEVELS = 0 | 8 | 12: number of coarse levels whose axis-0 duplicates are merged before the reduction
+  // (default 8; 0 switches the merging off for A/B runs); MRI_BWD_CONTIGUOUS=0 restores the grid-stride tile walk
   static const int merge_nt2 = [] {
     const char* e = getenv("MRI_BWD_MERGE_LEVELS");
-    return (e && atoi(e) == 0) ? 0 : 2;
+    const int v = e ? atoi(e) : 8;
+    return v <= 0 ? 0 : v >= 12 ? 3 : 2;
   }();
   static const bool contiguous = [] { const char* e = getenv("MRI_BWD_CONTIGUOUS"); return !e || atoi(e) != 0; }();
 #define CALL(DV, ACTV, MV, CV) launch_fused_bwd<DV, 32, 64, ACTV, MV, CV>(enc, n, w1, b1, w2, pre2, grad_y, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2, grad_b2, s)
-#define CALL_M(DV, ACTV) (merge_nt2 == 0 ? (contiguous ? CALL(DV, ACTV, 0, true) : CALL(DV, ACTV, 0, false)) \
-                                         : (contiguous ? CALL(DV, ACTV, 2, true) : CALL(DV, ACTV, 2, false)))
+#define CALL_M(DV, ACTV) (!contiguous ? CALL(DV, ACTV, 2, false) : merge_nt2 == 0 ? CALL(DV, ACTV, 0, true) : merge_nt2 == 2 ? CALL(DV, ACTV, 2, true) : CALL(DV, ACTV, 3, true))
   if (dim == 4 && act1 == MRI_ACT_GELU) return CALL_M(4, MRI_ACT_GELU);
   if (dim == 4 && act1 == MRI_ACT_RELU) return CALL_M(4, MRI_ACT_RELU);
   if (dim == 3 && act1 == MRI_ACT_GELU) return CALL_M(3, MRI_ACT_GELU);

@@ -93,13 +93,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) hashdecoder_mma_fwd_kernel(con
         const float* __restrict__ tbl = tables + lv.offset;
         // one branch per level (a few coarse levels have non-power-of-two row counts), both rows inside it: the 16
         // gathers of a level are straight-line code and go out back-to-back
-        if (lv.is_pow2) {
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) part[which][rr] = encode_half_level<D, 2, true>(make_cell<D>(xv[rr], lv), b0, lv, tbl);
-        } else {
-#pragma unroll
-          for (int rr = 0; rr < 2; ++rr) part[which][rr] = encode_half_level<D, 2, false>(make_cell<D>(xv[rr], lv), b0, lv, tbl);
-        }
+        encode_half_level_rows<D>(make_cell<D>(xv[0], lv), make_cell<D>(xv[1], lv), b0, lv, tbl, part[which][0], part[which][1]);
       }
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {

@@ -27,7 +27,7 @@ constexpr int MMA_PAD = 8;  // bf16 elements of row padding: conflict-free 32-bi
 // W (rows x cols, fp32, row-major in global) -> two padded bf16 planes in shared memory
 template <int ROWS, int COLS>
 __device__ __forceinline__ void stage_planes(const float* __restrict__ w, __nv_bfloat16* hi, __nv_bfloat16* lo, bool transpose) {
-  for (int e = threadIdx.x; e < ROWS * COLS; e += DEC_THREADS) {
+  for (int e = threadIdx.x; e < ROWS * COLS; e += blockDim.x) {
     const int r = e / COLS, c = e - r * COLS;
     const float v = __ldg(w + e);
     const __nv_bfloat16 h = __float2bfloat16_rn(v);

@@ -34,13 +34,24 @@ def create_mgrid(shape: Sequence[int]) -> torch.Tensor:
 class DeviceBatchLoader:
     """Iterable of (coords, pixels) batches cut from tensors that already live on `device`.
 
-    ``shuffle=True`` draws a fresh permutation per epoch from ``generator`` (device-side randperm).
-    ``rank``/``world_size`` give each data-parallel rank a disjoint strided share of every epoch.
+    ``shuffle=True`` draws a fresh permutation per epoch from ``generator`` (device-side randperm); a batch is the set of
+    voxels at positions [i*B, (i+1)*B) of that permutation, exactly as with the reference's shuffled DataLoader.
+    ``rank``/``world_size`` give each data-parallel rank a disjoint strided share of every epoch; the permutation is
+    padded (wrapping around, like ``DistributedSampler``) to a multiple of ``world_size`` so that every rank sees the
+    SAME number of batches of the SAME sizes - the optimiser step is collective, a rank with one batch more would hang.
+
+    ``grid_shape`` (the C-order voxel grid the rows of ``coords`` enumerate) switches on *locality-ordered batches*:
+    inside a batch the samples are arranged with the axis-0 index running fastest (functional.locality_key).  The batch
+    SET is unchanged and the loss is a mean over the batch, so training is the same up to fp32 summation order, but
+    neighbouring rows of a batch now hit neighbouring hash-table rows: -32 % L2 sectors in the gather, and the scatter
+    can merge duplicate updates (csrc/hash_device.cuh).  One stable sort of small keys per epoch pays for it:
+    voxels are kept in locality order once, and an epoch's permutation is turned into (batch id per voxel) and
+    stably sorted by that id.
     """
 
     def __init__(self, coords: torch.Tensor, pixels: torch.Tensor, batch_size: int, shuffle: bool = False,
                  device: Optional[torch.device] = None, seed: int = 1337, rank: int = 0, world_size: int = 1,
-                 drop_last: bool = False):
+                 drop_last: bool = False, grid_shape: Optional[Sequence[int]] = None, locality: bool = True):
         self.device = torch.device(device) if device is not None else coords.device
         self.coords = coords.to(self.device)
         self.pixels = pixels.to(self.device)
@@ -52,21 +63,56 @@ class DeviceBatchLoader:
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
         self.epoch = 0
+        self._loc_order = None
+        if grid_shape is not None and locality and shuffle:
+            if int(np.prod(grid_shape)) != self.coords.shape[0]:
+                raise ValueError(f"grid_shape {tuple(grid_shape)} does not enumerate the {self.coords.shape[0]} rows of coords")
+            from .functional import locality_key
+            flat = torch.arange(self.coords.shape[0], device=self.device)
+            self._loc_order = torch.argsort(locality_key(flat, grid_shape, block=1))
 
     def _local_count(self) -> int:
         n = self.coords.shape[0]
-        return (n - self.rank + self.world_size - 1) // self.world_size
+        return (n + self.world_size - 1) // self.world_size
 
     def __len__(self) -> int:
         n = self._local_count()
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
+    def epoch_indices(self) -> torch.Tensor:
+        """This rank's sample indices of one shuffled epoch, batch after batch (advances the generator)."""
+        n, w, b = self.coords.shape[0], self.world_size, self.batch_size
+        perm = torch.randperm(n, device=self.device, generator=self._gen)  # perm[p] = voxel at position p
+        total = self._local_count() * w
+        if total > n:
+            perm = torch.cat([perm, perm[: total - n]])
+        if self._loc_order is None:
+            return perm[self.rank::w] if w > 1 else perm
+        # position of every voxel (a wrapped-around voxel has two; both are kept)
+        pos = torch.empty(n, dtype=torch.int64, device=self.device)
+        pos[perm[:n]] = torch.arange(n, device=self.device)
+        lo = self._loc_order
+        vox, p = lo, pos[lo]
+        if total > n:
+            # the few wrapped-around voxels appear a second time, at positions n, n+1, ...: merge them in locality order
+            extra = perm[n:]
+            rank_of = torch.empty(n, dtype=torch.int64, device=self.device)
+            rank_of[lo] = torch.arange(n, device=self.device)
+            vox = torch.cat([lo, extra])
+            p = torch.cat([p, torch.arange(n, total, device=self.device)])
+            merged = torch.argsort(rank_of[vox], stable=True)
+            vox, p = vox[merged], p[merged]
+        if w > 1:
+            mine = (p % w) == self.rank
+            vox, p = vox[mine], p[mine] // w
+        batch_id = (p // b).to(torch.int32)
+        _, order = torch.sort(batch_id, stable=True)   # few distinct keys; voxels stay in locality order inside a batch
+        return vox[order]
+
     def __iter__(self):
         n = self.coords.shape[0]
         if self.shuffle:
-            order = torch.randperm(n, device=self.device, generator=self._gen)
-            if self.world_size > 1:
-                order = order[self.rank::self.world_size]
+            order = self.epoch_indices()
             for i in range(len(self)):
                 idx = order[i * self.batch_size:(i + 1) * self.batch_size]
                 yield self.coords.index_select(0, idx), self.pixels.index_select(0, idx)
@@ -191,7 +237,7 @@ class MriDataModule(pl.LightningDataModule):
         if shuffle and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         return DeviceBatchLoader(ds.coords, ds.pixels, self.config.batch_size, shuffle=shuffle, device=self._dev(),
-                                 rank=rank, world_size=world)
+                                 rank=rank, world_size=world, grid_shape=getattr(ds, "shape", None))
 
     def train_dataloader(self):
         return self._loader(self.train_ds, True)

@@ -26,9 +26,20 @@ def activation_code(act) -> int:
     return _ACT_BY_NAME[act]
 
 
+_grad_write_epoch = 0  # bumped whenever a backward kernel is handed a .grad buffer to accumulate into
+
+
+def grad_write_epoch() -> int:
+    """Monotonic counter of direct gradient accumulations; optim.FusedAdam compares it with the value it saw when it
+    last cleared the gradient arena to know whether the arena is still all zeros."""
+    return _grad_write_epoch
+
+
 def _direct_grad(p: torch.Tensor) -> Optional[torch.Tensor]:
+    global _grad_write_epoch
     g = getattr(p, "grad", None)
     if g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape:
+        _grad_write_epoch += 1
         return g
     return None
 
@@ -60,12 +71,21 @@ class _TableLayout:
         self.key = ptrs
 
 
+def _no_coordinate_gradient(ctx, what: str) -> None:
+    """The reference feeds coordinates from a DataLoader and never differentiates with respect to them (SURVEY 8a-6);
+    the kernels produce table gradients only.  Asking for d/dx must fail loudly, not return a silent None."""
+    if ctx.needs_input_grad[0]:
+        raise MriB200Error(f"{what}: the gradient with respect to the input coordinates is not implemented "
+                           f"(detach the coordinates; only the hash tables and the decoder receive gradients)")
+
+
 class HashGridFn(torch.autograd.Function):
     """encoding.py:108-128,190-191 forward; autograd of :127-128 backward (tables only - the
     reference never needs d/dx because coordinates come from a DataLoader)."""
 
     @staticmethod
     def forward(ctx, x, grid, *tables):
+        _no_coordinate_gradient(ctx, "hash-grid encoding")
         n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
         x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
         for t in tables:
@@ -236,6 +256,7 @@ class HashDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, grid, w1, b1, w2, b2, act1: int, act2: int, *tables):
+        _no_coordinate_gradient(ctx, "fused hash-grid + decoder")
         n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
         x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
         n = x2.shape[0]

@@ -42,6 +42,25 @@ def _fusable_activation(mod) -> Any:
     return None
 
 
+def sync_batchnorm_(module: nn.Module) -> int:
+    """Under data-parallel training (torch.distributed initialised, world_size > 1) replace every BatchNorm1d by a
+    SyncBatchNorm that shares its parameters and buffers (same state_dict keys).  The shipped HashMLP decoder has
+    BatchNorm (models.py:718-739): per-rank batch statistics would make W-GPU training differ from single-GPU training
+    on the global batch, and the running statistics - buffers, which the gradient arena does not synchronise - would
+    drift apart between the replicas (a sharded sweep would then stitch slabs of slightly different decoders).
+    Returns the number of layers converted."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return 0
+    count = 0
+    for parent in module.modules():
+        for name, child in list(parent.named_children()):
+            if isinstance(child, nn.modules.batchnorm._BatchNorm) and not isinstance(child, nn.SyncBatchNorm):
+                parent._modules[name] = nn.SyncBatchNorm.convert_sync_batchnorm(child)
+                count += 1
+    return count
+
+
 class BaseMLP(pl.LightningModule):
     """Fully connected network, base class of the other models (models.py:20-95)."""
 
@@ -104,6 +123,7 @@ class BaseMLP(pl.LightningModule):
 
     def configure_optimizers(self):
         # torch.optim.Adam(self.parameters(), lr) semantics (models.py:68-70), one fused kernel
+        sync_batchnorm_(self)
         self.optimizer = FusedAdam(self.parameters(), lr=self.lr)
         return self.optimizer
 
@@ -250,7 +270,9 @@ class SirenNet(BaseMLP):
         return "bf16x3" if mode == "auto" else mode
 
     def forward(self, x):
-        mode = self._tensor_core_mode()
+        # d/dx exists on the fp32 CUDA-core path only: a caller that differentiates with respect to the coordinates gets
+        # the same behaviour whatever the hidden width is
+        mode = None if (torch.is_grad_enabled() and x.requires_grad) else self._tensor_core_mode()
         if mode is not None:
             from . import siren_fused
             return siren_fused.forward(self, x, mode)

@@ -51,6 +51,7 @@ class FlatArena:
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         total = (total + pad_to - 1) // pad_to * pad_to
         self.numel = total
+        self.had_grads = any(p.grad is not None for p in self.params)  # copied into the arena below: it is not all zeros
         self.data_hdl = self.grad_hdl = None
         if symmetric_group is not None:
             import torch.distributed._symmetric_memory as symm
@@ -149,11 +150,33 @@ class FusedAdam(torch.optim.Optimizer):
         self.step_count = 0
         self.grad_average = grad_average
         self.fuse_zero_grad = fuse_zero_grad
-        self._grads_clean = True  # freshly allocated arena gradient is zero
+        # "the gradient arena is all zeros" is tracked with a token, not a guess: functional.grad_write_epoch() moves
+        # whenever a backward kernel accumulates into a .grad buffer, post-accumulate hooks catch autograd's own
+        # accumulations (BatchNorm parameters etc.), and gradients that existed before the arena was built were copied in
+        self._clean_token = None
+        self._torch_dirty = False
+        for p in self.arena.params:
+            p.register_post_accumulate_grad_hook(self._mark_dirty)
+        self._grads_clean = not self.arena.had_grads
         self.allreduce_count = 0
         self._overlap = None
         self._step_dev = None   # device-side step counter + {lr/bc1, sqrt(bc2)} scratch: set by use_device_step()
         self._hyper_dev = None
+
+    def _mark_dirty(self, _param=None) -> None:
+        self._torch_dirty = True
+
+    @property
+    def _grads_clean(self) -> bool:
+        from . import functional as Fn
+        return self._clean_token is not None and self._clean_token == Fn.grad_write_epoch() and not self._torch_dirty
+
+    @_grads_clean.setter
+    def _grads_clean(self, clean: bool) -> None:
+        from . import functional as Fn
+        self._clean_token = Fn.grad_write_epoch() if clean else None
+        if clean:
+            self._torch_dirty = False
 
     # -- distributed
     def _world(self) -> int:
@@ -311,12 +334,17 @@ class FusedAdam(torch.optim.Optimizer):
             self._step_dev.fill_(count)
 
     def zero_grad(self, set_to_none: bool = False):
-        """Gradients stay views of the arena.  The first zero_grad() after a fused step is free (the
-        Adam kernel already cleared them); any other call clears the arena."""
-        if not self._grads_clean:
+        """Gradients stay views of the arena.  zero_grad() is free while the arena is known to be all zeros (right after a
+        fused step, which clears it, or after another zero_grad()) and NO backward has accumulated into it since -
+        e.g. ``step(); backward(); zero_grad()`` does clear the new gradients."""
+        intact = self.arena.intact()
+        if not self._grads_clean or not intact:
             self.arena.grad.zero_()
-        self.arena.reattach_grads()
-        self._grads_clean = False
+        if not intact:
+            for p in self.arena.params:  # stale private gradients are dropped, not copied back into the cleared arena
+                p.grad = None
+            self.arena.reattach_grads()
+        self._grads_clean = True
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,

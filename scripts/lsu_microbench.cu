@@ -64,7 +64,12 @@ enum Op { RED_V2 = 0, RED_V4, RED_F32, LDG_64, LDG_128, N_OPS };
 static const char* op_name[] = {"red.v2.f32", "red.v4.f32", "red.f32", "ld.v2.f32", "ld.v4.f32"};
 
 template <int OP, int U>
-__global__ void __launch_bounds__(128) probe(float* __restrict__ table, uint32_t rows_mask, int pattern, int iters, float* sink) {
+__global__ void __launch_bounds__(128) probe(float* __restrict__ table, uint32_t rows_mask, int pattern, int iters, float* sink, int sm_mod) {
+  if (sm_mod > 1) {  // only every sm_mod-th SM works: separates a per-SM (LSU) limit from a chip-wide (L2) one
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid % sm_mod) return;
+  }
   const int lane = threadIdx.x & 31;
   const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const bool active = lane_active(pattern, lane);
@@ -95,16 +100,16 @@ __global__ void __launch_bounds__(128) probe(float* __restrict__ table, uint32_t
 }
 
 template <int OP>
-float run(float* table, uint32_t rows_mask, int pattern, int blocks, int iters, float* sink) {
+float run(float* table, uint32_t rows_mask, int pattern, int blocks, int iters, float* sink, int sm_mod = 1) {
   constexpr int U = 8;
   cudaEvent_t a, b;
   CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-  probe<OP, U><<<blocks, 128>>>(table, rows_mask, pattern, iters / 4, sink);
+  probe<OP, U><<<blocks, 128>>>(table, rows_mask, pattern, iters / 4, sink, sm_mod);
   CK(cudaDeviceSynchronize());
   float best = 1e30f;
   for (int rep = 0; rep < 3; ++rep) {
     CK(cudaEventRecord(a));
-    probe<OP, U><<<blocks, 128>>>(table, rows_mask, pattern, iters, sink);
+    probe<OP, U><<<blocks, 128>>>(table, rows_mask, pattern, iters, sink, sm_mod);
     CK(cudaEventRecord(b));
     CK(cudaEventSynchronize(b));
     float ms;
@@ -147,5 +152,19 @@ int main(int argc, char** argv) {
       }
     }
   }
+  printf("\n-- per-SM or chip-wide?  red.v2.f32 with only every k-th SM active (4 blocks of 128 threads per SM) --\n");
+  for (int sm_mod = 1; sm_mod <= 8; sm_mod *= 2)
+    for (int p : {int(SPREAD), int(PAIR16B), int(CONTIG), int(CHAIN_LINE)}) {
+      const float ms = run<RED_V2>(table, rows - 1, p, 4 * sms, 256, sink, sm_mod);
+      const double ns = ms * 1e6 / (4.0 * 4 * 256 * 8);
+      printf("every %d-th SM  %-34s %9.4f ms %8.2f ns/warp-op/SM %8.1f cyc\n", sm_mod, pattern_name[p], ms, ns, ns * 1.965);
+    }
+  printf("\n-- per-SM or chip-wide?  red.v2.f32 with only every k-th SM active (4 blocks of 128 threads per SM) --\n");
+  for (int sm_mod = 1; sm_mod <= 8; sm_mod *= 2)
+    for (int p : {int(SPREAD), int(PAIR16B), int(CONTIG), int(CHAIN_LINE)}) {
+      const float ms = run<RED_V2>(table, rows - 1, p, 4 * sms, 256, sink, sm_mod);
+      const double ns = ms * 1e6 / (4.0 * 4 * 256 * 8);
+      printf("every %d-th SM  %-34s %9.4f ms %8.2f ns/warp-op/SM %8.1f cyc\n", sm_mod, pattern_name[p], ms, ns, ns * 1.965);
+    }
   return 0;
 }

@@ -58,10 +58,19 @@ def _worker(rank, world, init_file, out_dir):
         mine = torch.cat([a for a, _ in ld]).flatten().tolist()
         shares = [None] * world
         dist.all_gather_object(shares, mine)
+        # n % world != 0 with a full last batch on one rank only (n = 2*16+1) used to give rank 0 two batches
+        # and rank 1 one - a hang in the collective optimiser step.  Every rank must see the same batch sizes.
+        odd = torch.arange(33, dtype=torch.float32).reshape(-1, 1)
+        sizes = [None] * world
+        for grid in (None, (11, 3)):
+            ld2 = datamodules.DeviceBatchLoader(odd, odd.clone(), 16, shuffle=True, device="cpu", seed=4, rank=rank, world_size=world,
+                                                grid_shape=grid)
+            dist.all_gather_object(sizes, [a.shape[0] for a, _ in ld2] + [len(ld2)])
+            assert all(s == sizes[0] for s in sizes) and sizes[0] == [16, 1, 2], sizes
         if rank == 0:
             np.save(os.path.join(out_dir, "result.npy"),
                     np.asarray([ok_grad, scale == 0.5, spans == [sweep.slab_range(105, r, world) for r in range(world)],
-                                sorted(sum(shares, [])) == list(range(101))], dtype=bool))
+                                sorted(set(sum(shares, []))) == list(range(101)) and all(len(sh) == 51 for sh in shares)], dtype=bool))
     finally:
         dist.destroy_process_group()
 

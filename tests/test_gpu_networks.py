@@ -172,6 +172,55 @@ def test_fused_adam_odd_sizes_and_arena_views():
         torch.testing.assert_close(p.detach().cpu(), r.detach(), rtol=2e-6, atol=1e-8)
 
 
+def test_zero_grad_never_skips_a_dirty_arena():
+    """zero_grad() may skip its memset only while the gradient arena is provably all zeros.
+    (a) step(); backward(); zero_grad(); backward() must not double-accumulate;  (b) gradients that existed before the
+    optimiser was built are copied into the arena and must be cleared by the first zero_grad();  (c) autograd's own
+    accumulation (a parameter used by plain torch ops) also marks the arena dirty."""
+    from mri_interpolation_b200 import models
+    kw = dict(dim_in=3, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=4,
+              finest_resolution=64, dim_hidden=64, dim_out=1, n_layers=2)
+    torch.manual_seed(3)
+    x, y = torch.rand(777, 3, device=DEV), torch.rand(777, 1, device=DEV)
+
+    def grads(net):
+        return torch.cat([p.grad.reshape(-1) for n_, p in net.named_parameters() if not n_.startswith("layers.")]).clone()
+
+    # (b) stale gradients before configure_optimizers()
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, lr=5e-3).to(DEV)
+    net.training_step((x, y), 0).backward()           # private .grad tensors, not in any arena yet
+    opt = net.configure_optimizers()
+    assert not opt._grads_clean
+    opt.zero_grad()
+    assert float(opt.arena.grad.abs().max()) == 0.0
+    net.training_step((x, y), 0).backward()
+    single = grads(net)
+    # (a) step -> backward -> zero_grad -> backward
+    opt.step()
+    assert opt._grads_clean                              # the fused step cleared the arena
+    net.training_step((x, y), 1).backward()
+    assert not opt._grads_clean                          # ... and this backward dirtied it again
+    opt.zero_grad()
+    assert float(opt.arena.grad.abs().max()) == 0.0
+    net.training_step((x, y), 2).backward()
+    once = grads(net)
+    opt.zero_grad()
+    opt.zero_grad()                                      # free: nothing accumulated in between
+    net.training_step((x, y), 2).backward()
+    torch.testing.assert_close(grads(net), once, rtol=1e-5, atol=1e-9)
+    assert float(single.abs().max()) > 0
+    # (c) torch-side accumulation
+    ps = [torch.nn.Parameter(torch.randn(50, device=DEV))]
+    from mri_interpolation_b200.optim import FusedAdam
+    o2 = FusedAdam(ps, lr=1e-2)
+    assert o2._grads_clean
+    (ps[0] * 2).sum().backward()
+    assert not o2._grads_clean
+    o2.zero_grad()
+    assert float(ps[0].grad.abs().max()) == 0.0
+
+
 def test_training_steps_track_the_oracle():
     """5 full steps (hash grid + decoder + MSE + Adam) from identical init and batches: parameters stay
     within summation-order noise of the oracle's torch.optim.Adam run."""

@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from conftest import SAMPLE, SIREN_CASES, load_golden
+from mri_interpolation_b200 import functional as Fn
 from mri_interpolation_b200 import config, datamodules, distributed, encoding, metrics, models, nifti, sweep
 from mri_interpolation_b200.pl_compat import pl
 
@@ -143,7 +144,42 @@ def test_device_batch_loader_epoch_semantics():
         ld = datamodules.DeviceBatchLoader(coords, pix, 8, shuffle=True, device="cpu", seed=5, rank=r, world_size=3)
         shards.append(torch.cat([x for x, _ in ld]).flatten())
     allv = torch.cat(shards)
-    assert allv.shape[0] == 103 and torch.equal(allv.sort().values, coords.flatten())
+    # padded (wrap-around) to a multiple of the world size: every rank sees the same number and sizes of batches
+    assert [s.shape[0] for s in shards] == [35, 35, 35] and torch.equal(allv.unique(), coords.flatten())
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("shape,bs", [((7, 5, 3), 16), ((6, 4, 2, 3), 25), ((9, 3), 27)])
+def test_locality_ordered_batches_are_the_same_sets_in_axis0_fastest_order(world, shape, bs):
+    """grid_shape switches on locality-ordered batches: per batch the SAME voxels as the plain shuffled loader (same
+    seed), ordered with the axis-0 index fastest; ranks see equally many, equally sized batches."""
+    n = int(np.prod(shape))
+    coords = torch.arange(n, dtype=torch.float32).reshape(-1, 1)
+    lens = set()
+    for r in range(world):
+        plain = datamodules.DeviceBatchLoader(coords, coords.clone(), bs, shuffle=True, device="cpu", seed=9, rank=r, world_size=world)
+        local = datamodules.DeviceBatchLoader(coords, coords.clone(), bs, shuffle=True, device="cpu", seed=9, rank=r, world_size=world,
+                                              grid_shape=shape)
+        for epoch in range(2):
+            pb, lb = [x.flatten().long() for x, _ in plain], [x.flatten().long() for x, _ in local]
+            lens.add(tuple(b.shape[0] for b in lb))
+            assert len(pb) == len(lb) == len(local)
+            for a, b in zip(pb, lb):
+                assert torch.equal(a.sort().values, b.sort().values)
+                key = Fn.locality_key(b, shape, block=1)
+                assert bool((key[1:] >= key[:-1]).all())
+    assert len(lens) == 1  # identical batch sizes on every rank and in every epoch
+
+
+def test_locality_key_walks_axis0_fastest():
+    shape = (5, 4, 3)
+    idx = torch.arange(int(np.prod(shape)))
+    order = torch.argsort(Fn.locality_key(idx, shape, block=1))
+    v0, v1, v2 = idx[order] // 12, idx[order] // 3 % 4, idx[order] % 3
+    assert v0[:5].tolist() == [0, 1, 2, 3, 4] and v1[:5].tolist() == [0] * 5 and v2[:5].tolist() == [0] * 5
+    assert v1[5:10].tolist() == [1] * 5 and v2[:20].tolist() == [0] * 20 and v2[20:40].tolist() == [1] * 20
+    s = Fn.locality_sort(torch.tensor([[59, 0, 13, 12, 1]]), shape, block=1)
+    assert s.tolist() == [[0, 12, 1, 13, 59]]
 
 
 def test_slab_and_batch_partition():
