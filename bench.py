@@ -2,22 +2,28 @@
 """Benchmark of the coordinate-network hot path (BASELINE.json metric: training coords/s, plus inference
 voxels/s, with % of roofline and the reference's CPU path timed beside it).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch-log2 B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch-log2 B] [--workload NAME]
 
-Workload (configs[1] of BASELINE.json, named in `config.workload`): hash-grid encoder G4
+Headline workload (configs[1] of BASELINE.json, named in `config.workload`): hash-grid encoder G4
 (config/hash_config.json: L=16, F=2, T=2^19, base 16, x1.4 -> finest 2489; 15 279 648 table params)
 + 2-layer GELU decoder (64 hidden), fitted to the sample ankle volume (352x352x6x15, x,y,z,t coords),
 fp32, Adam lr 5e-3, 2^B coordinates per step PER GPU (weak scaling; N>1 exchanges the flat gradient arena once
-per step inside the sharded Adam kernel).  One step = 5 kernels: sample voxel indices -> synthesise coords /
-gather intensities -> hash encode + decoder (one kernel) -> MSE -> decoder backward + hash scatter (one
-kernel) -> fused Adam [with the reduce-scatter / all-gather over NVLink at N>1].
+per step inside the sharded Adam kernel).  One step = 5 kernels: synthesise coords / gather intensities from the
+step's voxel indices -> hash encode + decoder (one kernel) -> MSE -> decoder backward + hash scatter (one kernel)
+-> fused Adam [with the reduce-scatter / all-gather over NVLink at N>1].  The voxel indices are shuffled epochs
+(a permutation of the volume cut into batches, as the reference's DataLoader does), each batch arranged in locality
+order (axis-0 index fastest: same sets, see datamodules.ShuffledEpochs); they are drawn before the timed region and
+their amortised cost is reported as `sampler_ms_per_batch`.
 
-value : device-resident inputs, CUDA-event timing, max over ranks.
+value : device-resident inputs, CUDA-event timing of EXACTLY --steps steps, max over ranks.  `sustained` repeats the
+        same steps for >= 0.6 s (the clock samples cover the timed region plus that window).
 e2e   : same step through the public LightningModule API with HOST (pinned) batches: H2D copy of the
         batch and D2H read of the loss inside the timed region.
 roofline : dominant kernel (decoder backward fused with the hash-grid scatter) timed alone with CUDA events, L2
         flushed between launches; algorithmic bytes / duration against MEASURED_PEAKS.json's HBM copy bandwidth.
-cpu_baseline : the oracle port of the reference's PyTorch path on this box's host cores (bounded sample).
+workloads : short legs of the other BASELINE configs (1: SIREN on the ankle volume, 4: synthetic 256^3x32 hash,
+        5: wide SIREN 8x1024 on the tcgen05 path), each with its own roofline and clocks.
+cpu_baseline / --impl reference : the reference's own classes (baseline/_ref, unmodified) on this box's host cores.
 """
 from __future__ import annotations
 
@@ -39,9 +45,11 @@ SAMPLE = os.path.join(ROOT, "data", "sample_ankle_dyn_mri.nii.gz")
 SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (config 3)
 PRIMING_STEPS = 15  # allocator priming before the W warm-up steps (reported in config)
 HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of hashdecoder_mma_bwd_kernel at 2^19 coords (ncu --set full,
-# profiles/r01_ncu_full_fused_hashdecoder.csv): 137.9 MB read + 256.8 MB written
-FUSED_BWD_DRAM_BYTES = 394.6e6
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^19 locality-ordered coords, from the ncu --set full
+# capture of THIS kernel version committed as profiles/r02_ncu_full_fused_hashdecoder.csv (same command, --steps 3)
+NCU_DRAM_BYTES = {"hashdecoder_bwd": 142.2e6 + 184.7e6, "hashdecoder_fwd": 86.7e6 + 60.0e6}
+NCU_SOURCE = "profiles/r02_ncu_full_fused_hashdecoder.csv"
+SUSTAIN_SECONDS = 0.6
 
 
 WORKLOADS = {
@@ -49,12 +57,13 @@ WORKLOADS = {
     "ankle_hash": ("hash-grid G4 (L16 F2 T2^19 base16 finest2489, 15.28M table params) + 2x64 GELU decoder fitted to "
                    "sample_ankle_dyn_mri.nii.gz (352x352x6x15, xyzt coords), Adam lr 5e-3", 19),
     "synthetic_hash": ("config 4: hash-grid G4 + 2x64 GELU decoder on a synthetic 256^3 x 32-frame volume (536.9M voxels, "
-                       "sum of separable sinusoids + noise, generated on device), Adam lr 5e-3", 19),
+                       "sum of separable sinusoids + noise, generated on device), i.i.d. voxel indices per step, Adam lr 5e-3", 19),
     "siren_wide": ("config 5: SirenNet 3 -> 1024 x 8 -> 1 (w0 30) on a synthetic 512^3 volume, coords in [-1,1], "
                    "tensor-core split-precision mode bf16x3 (fp32 parity), Adam lr 1e-4", 17),
     "siren_ankle": ("config 1: SirenNet 4 -> 256 x 5 -> 1 (w0 30) on sample_ankle_dyn_mri.nii.gz, tensor-core "
                     "split-precision mode bf16x3 (fp32 parity), Adam lr 1e-4", 18),
 }
+EXTRA_LEGS = ("siren_wide", "synthetic_hash", "siren_ankle")
 
 
 def parse():
@@ -66,10 +75,11 @@ def parse():
     ap.add_argument("--batch-log2", type=int, default=None, help="log2 coordinates per step per GPU (default per workload)")
     ap.add_argument("--workload", default="ankle_hash", choices=list(WORKLOADS),
                     help="ankle_hash = BASELINE configs[1] (default, the driver's bench line); the others are configs 1/4/5")
-    ap.add_argument("--cpu-batch-log2", type=int, default=15)
+    ap.add_argument("--cpu-batch-log2", type=int, default=19, help="coords per CPU step of the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the short legs of configs 1/4/5 after the headline")
     args = ap.parse_args()
     if args.batch_log2 is None:
         args.batch_log2 = WORKLOADS[args.workload][1]
@@ -81,8 +91,8 @@ def peaks():
     if os.path.isfile(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return p, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -92,7 +102,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
+        self.index, self.proc, self.path, self.skip = index, None, None, 0
 
     def start(self):
         if os.environ.get("MRI_BENCH_NO_CLOCKS") == "1":
@@ -125,7 +135,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         try:
-            lines = open(self.path).read().splitlines()[getattr(self, "skip", 0):]
+            lines = open(self.path).read().splitlines()[self.skip:]
             os.unlink(self.path)
         except Exception:  # noqa: BLE001
             lines = []
@@ -147,48 +157,71 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def oracle_step_fn(batch_log2: int):
-    """One training step of the reference's PyTorch CPU path (oracle port): G4 + 2x64 GELU decoder + Adam."""
+def reference_step_fn(batch_log2: int):
+    """One training step of the reference's OWN classes on the CPU: `encoding.MultiResHashGrid` (unmodified, imported from
+    baseline/_ref) in the G4 geometry + the notebook's Linear -> GELU decoder blocks (nb cell 37; the shipped
+    HashMLP.forward calls a ModuleList and cannot run) + F.mse_loss + torch.optim.Adam(lr 5e-3), batches cut from the
+    sample volume exactly like MriImage does (linspace coords, min-max intensities).  Returns (step, n, kind)."""
     import torch.nn.functional as F
-    from oracle import networks, sweep as osweep
     from mri_interpolation_b200 import nifti
-    torch.manual_seed(1337)
-    params, levels = networks.hashmlp_init(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, **G4)
-    params = {k: v.requires_grad_() for k, v in params.items() if not k.startswith("layers.")}
-    opt = torch.optim.Adam(list(params.values()), lr=5e-3)
     vol = torch.from_numpy(nifti.load(SAMPLE).get_fdata(np.float32))
-    pixels = osweep.normalise_intensities(vol)
-    axes = [osweep.axis_values(s) for s in vol.shape]
+    pix = vol.flatten()
+    pix = ((pix - pix.min()) / (pix.max() - pix.min())).unsqueeze(-1)
+    axes = [torch.linspace(0, 1, s) for s in vol.shape]
     shape = torch.tensor(vol.shape)
-    gen = torch.Generator().manual_seed(1337)
     n = 1 << batch_log2
+    gen = torch.Generator().manual_seed(1337)
+    torch.manual_seed(1337)
+    from baseline import load_reference
+    if load_reference.available():
+        ref_encoding, _ = load_reference.load()
+        encoder = ref_encoding.MultiResHashGrid(4, **G4)
+        decoder = torch.nn.Sequential(torch.nn.Linear(32, 64), torch.nn.GELU(), torch.nn.Linear(64, 1), torch.nn.GELU())
+        params = list(encoder.parameters()) + list(decoder.parameters())
+        forward = lambda x: decoder(encoder(x))  # noqa: E731
+        kind = "reference"
+    else:  # no copy of the reference on this box: the oracle port of the same arithmetic
+        from oracle import networks
+        p, levels = networks.hashmlp_init(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, **G4)
+        p = {k: v.requires_grad_() for k, v in p.items() if not k.startswith("layers.")}
+        params = list(p.values())
+        forward = lambda x: networks.hashmlp_forward(x, p, levels, 2, False)  # noqa: E731
+        kind = "port"
+    opt = torch.optim.Adam(params, lr=5e-3)
 
     def step():
-        idx = torch.randint(0, pixels.shape[0], (n,), generator=gen)
+        idx = torch.randint(0, pix.shape[0], (n,), generator=gen)
         rem, cols = idx.clone(), []
         for d in range(3, -1, -1):
             cols.append(axes[d][rem % shape[d]])
             rem = rem // shape[d]
         x = torch.stack(cols[::-1], dim=-1)
         opt.zero_grad()
-        loss = F.mse_loss(pixels[idx], networks.hashmlp_forward(x, params, levels, 2, False))
+        loss = F.mse_loss(pix[idx], forward(x))
         loss.backward()
         opt.step()
         return float(loss.detach())
 
-    return step, n
+    return step, n, kind
 
 
-def time_oracle(batch_log2: int, steps: int, warmup: int):
+def time_reference(batch_log2: int, steps: int, warmup: int):
     torch.set_num_threads(os.cpu_count() or 1)
-    step, n = oracle_step_fn(batch_log2)
+    step, n, kind = reference_step_fn(batch_log2)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return n / dt, dt, n
+    return n / dt, dt, n, kind
+
+
+def cpu_sample_text(kind, steps, log2, dt):
+    what = ("the reference's own encoding.MultiResHashGrid (baseline/_ref, unmodified) + nb-cell-37 Linear/GELU decoder + "
+            "F.mse_loss + torch.optim.Adam" if kind == "reference" else
+            "oracle port of the reference's PyTorch CPU path: hash G4 + decoder + MSE + torch.optim.Adam")
+    return f"{steps} steps of 2^{log2} coords of the same training step ({what}), {dt * 1e3:.0f} ms/step"
 
 
 def run_reference(args):
@@ -199,33 +232,32 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is implemented for the default "
                           "workload (ankle_hash, BASELINE configs[1]) only"}))
         return
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    value, dt, n = time_oracle(args.cpu_batch_log2, steps, warm)
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    value, dt, n, kind = time_reference(args.cpu_batch_log2, steps, warm)
     cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "sample_ankle_dyn_mri.nii.gz (bundled) + random-init weights",
-        "config": workload_config(args, cpu_sample=n),
-        "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of 2^{args.cpu_batch_log2} coords (oracle port of the reference's "
-                                   f"PyTorch CPU path: hash G4 + decoder + MSE + torch.optim.Adam)"},
+        "config": workload_config(args, "ankle_hash", args.cpu_batch_log2, 1, cpu_sample=n),
+        "cpu_baseline": {"value": value, "unit": "coords/s", "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(kind, steps, args.cpu_batch_log2, dt)},
         "e2e": {"value": value, "unit": "coords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args, cpu_sample=None):
-    cfg = {"workload": WORKLOADS[args.workload][0], "workload_name": args.workload,
-           "batch_per_gpu": 1 << args.batch_log2, "global_batch": (1 << args.batch_log2) * args.gpus,
-           "parallelism": f"dp{args.gpus}" + (" (fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory; "
-                                                 "NCCL all-reduce when symmetric memory is unavailable)"
-                                                 if args.gpus > 1 else ""), "l2": "inputs larger than L2: every step streams the whole p/g/m/v arena through Adam "
-                                                  "(hash: 489 MB/step) plus per-batch activations (SIREN: > 1 GB/layer)"}
+def workload_config(args, name, batch_log2, world, cpu_sample=None):
+    cfg = {"workload": WORKLOADS[name][0], "workload_name": name,
+           "batch_per_gpu": 1 << batch_log2, "global_batch": (1 << batch_log2) * world,
+           "parallelism": f"dp{world}" + (" (fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory; "
+                                          "NCCL all-reduce when symmetric memory is unavailable)" if world > 1 else ""),
+           "l2": "inputs larger than L2: every step streams the whole p/g/m/v arena through Adam "
+                 "(hash: 489 MB/step) plus per-batch activations (SIREN: > 1 GB/layer)"}
     cfg["allocator_priming_steps_before_warmup"] = PRIMING_STEPS
-    cfg["batch_order"] = os.environ.get("MRI_BATCH_ORDER", "axis0") + (": i.i.d. uniform voxel indices, each batch arranged with the "
-                                                                        "axis-0 index fastest (same sets; the loss is order-invariant)")
+    cfg["batch_order"] = (os.environ.get("MRI_BATCH_ORDER", "axis0") + ": every batch arranged with the axis-0 voxel index "
+                          "fastest (same sets; the loss is order-invariant)")
     if cpu_sample:
         cfg["cpu_sample_coords_per_step"] = cpu_sample
     return cfg
@@ -246,16 +278,16 @@ def synthetic_volume(shape, dev, seed=1337):
             view[d] = s
             term = term * torch.sin(torch.linspace(0, 1, s, device=dev) * (6.2831853 * f) + ph).reshape(view)
         out += term
+        del term
     out += 0.04 * torch.rand(shape, device=dev, generator=g)
     out = (out - out.min()) / (out.max() - out.min())
     return out.flatten()
 
 
-def build_workload(args, dev, rank):
+def build_workload(name, dev):
     from mri_interpolation_b200 import models, nifti
     from mri_interpolation_b200 import functional as Fn
     torch.manual_seed(1337)
-    name = args.workload
     info = {}
     if name in ("ankle_hash", "synthetic_hash"):
         model = models.HashMLP(dim_in=4, dim_hidden=64, dim_out=1, n_layers=2, lr=5e-3, batch_norm=False, **G4).to(dev)
@@ -287,53 +319,68 @@ def build_workload(args, dev, rank):
     return model, sampler, info
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def draw_index_ring(name, sampler, info, n, ring, dev, rank, world):
+    """(ring, n) voxel indices drawn before the timed region + what drawing one batch costs (ms, amortised)."""
+    from mri_interpolation_b200 import functional as Fn
+    from mri_interpolation_b200.datamodules import ShuffledEpochs
+    order = os.environ.get("MRI_BATCH_ORDER", "axis0")
+    shape = info["shape"]
+    if "ankle" in name:
+        # shuffled epochs of the sample volume, as the reference's DataLoader(shuffle=True): a permutation cut into batches
+        # (data-parallel ranks take disjoint strided shares), locality-ordered inside each batch
+        epochs = ShuffledEpochs(sampler.total, n, dev, seed=1337, rank=rank, world_size=world,
+                                grid_shape=shape if order != "none" else None)
+        full = epochs.local_count() // n  # whole batches per epoch
+        if full == 0:
+            raise SystemExit(f"batch of 2^{int(np.log2(n))} per GPU exceeds this rank's share of the volume")
+        parts, got, n_epochs = [], 0, 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        while got < ring:
+            parts.append(epochs.epoch()[: full * n].reshape(full, n))
+            got += full
+            n_epochs += 1
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / (n_epochs * full)
+        index = torch.cat(parts)[:ring].contiguous()
+        how = (f"ShuffledEpochs: {full} whole batches per epoch of this rank's {epochs.local_count()} voxels, locality order "
+               f"{order}; ms = epoch generation / batches per epoch")
+    else:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1337 + rank)
 
-    from mri_interpolation_b200 import _lib, distributed, sweep
+        def draw():
+            i = torch.randint(0, sampler.total, (n,), device=dev, generator=gen)
+            return Fn.locality_sort(i, shape, block=1) if order != "none" else i
+
+        index = torch.stack([draw() for _ in range(ring)])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            draw()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) / 4 * 1e3
+        how = f"i.i.d. torch.randint per batch (SURVEY 8d config 4/5), locality order {order} by one argsort per batch"
+    return index, ms, how
+
+
+def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world, *, e2e=True, infer=True, kernels=True):
+    """One workload: timed training steps (+ sustained window with clocks), e2e, inference sweep, isolated kernels."""
+    import torch.distributed as dist
+    from mri_interpolation_b200 import _lib, sweep
     from mri_interpolation_b200.datamodules import PrefetchLoader
 
-    rank, local_rank, world = distributed.init_from_env("nccl")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
-    import torch.distributed as dist
-
-    model, sampler, info = build_workload(args, dev, rank)
-    is_hash = args.workload.endswith("hash")
+    model, sampler, info = build_workload(name, dev)
+    is_hash = name.endswith("hash")
     opt = model.configure_optimizers()
     # bucketed/overlapped all-reduce is available but measured SLOWER at W=2 (1.608 vs 1.561 ms/step): the scatter
-    # backward and NCCL's copy kernels both saturate the L2, so the default stays one all-reduce after backward
+    # backward and NCCL's copy kernels both saturate the L2, so the default stays one exchange after backward
     if is_hash and world > 1 and os.environ.get("MRI_DP_OVERLAP") == "1":
         opt.enable_overlap(model.encoder, n_groups=4)
-    n = 1 << args.batch_log2
+    n = 1 << batch_log2
     dim = len(info["shape"])
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1337 + rank)
-    total_steps = args.steps + args.warmup
-    # the shuffled index stream is drawn up front (like a DataLoader sampler), as a ring of 32 batches
     ring = 32
-    index = torch.randint(0, sampler.total, (ring, n), device=dev, generator=gen)
-    # locality-ordered batches (the loaders' default, datamodules.DeviceBatchLoader / functional.locality_sort): the SAME
-    # random voxel sets, arranged inside a batch with the axis-0 index fastest.  MRI_BATCH_ORDER=none keeps the drawn order.
-    from mri_interpolation_b200 import functional as Fn
-    batch_order = os.environ.get("MRI_BATCH_ORDER", "axis0")
-    if batch_order != "none":
-        index = Fn.locality_sort(index, info["shape"], block=int(batch_order[3:]) if batch_order.startswith("blk") else 1)
-    # what drawing + ordering one batch costs on the device (index generation is loader work outside the timed step;
-    # DeviceBatchLoader amortises it into one stable sort per epoch)
-    torch.cuda.synchronize()
-    _t0 = time.perf_counter()
-    for _ in range(8):
-        _i = torch.randint(0, sampler.total, (n,), device=dev, generator=gen)
-        if batch_order != "none":
-            _i = Fn.locality_sort(_i, info["shape"], block=1)
-    torch.cuda.synchronize()
-    sampler_ms = (time.perf_counter() - _t0) / 8 * 1e3
+    index, sampler_ms, sampler_how = draw_index_ring(name, sampler, info, n, ring, dev, rank, world)
 
     def step(i):
         x, y = sampler.batch(index[i % ring])
@@ -348,151 +395,160 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(first, count):
+        """`count` steps with the host's run-ahead bounded to two steps (a saturated launch queue starves NCCL's progress
+        thread and made multi-GPU SIREN steps ~25% slower); returns (device ms, last loss)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        inflight = []
+        ev0.record()
+        loss = None
+        for i in range(first, first + count):
+            loss = step(i)
+            ev = torch.cuda.Event()
+            ev.record()
+            inflight.append(ev)
+            if len(inflight) > 2:
+                inflight.pop(0).synchronize()
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), loss
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()  # nvidia-smi needs a few hundred ms to come up: started before the untimed steps, marked below
     for i in range(PRIMING_STEPS):  # untimed: lets torch's caching allocator reach its steady state (no cudaMalloc later)
         step(i)
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     barrier()
     clocks.mark()
     launches0 = _lib.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    inflight = []
-    trace = [] if os.environ.get("MRI_BENCH_TRACE") == "1" else None
-    for i in range(args.warmup, total_steps):
-        loss = step(i)
-        if trace is not None:
-            te = torch.cuda.Event(enable_timing=True)
-            te.record()
-            trace.append(te)
-        # bound the host's run-ahead to two steps (a saturated launch queue starves NCCL's progress thread and made
-        # multi-GPU SIREN steps ~25% slower); the GPU stays fed: the event waited on is two steps old
-        ev = torch.cuda.Event()
-        ev.record()
-        inflight.append(ev)
-        if len(inflight) > 2:
-            inflight.pop(0).synchronize()
-    ev1.record()
-    barrier()
+    ms, loss = run_steps(warmup, steps)
     launches = _lib.launch_count - launches0
-    ms = ev0.elapsed_time(ev1)
-    if trace:
-        sys.stderr.write("per-step ms: " + " ".join(f"{a.elapsed_time(b):.1f}" for a, b in zip([ev0] + trace[:-1], trace)) + "\n")
-    clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    # a timed region shorter than nvidia-smi's sampling period holds no clock sample: run the same steps again, untimed,
-    # for ~0.5 s on every rank (same count everywhere: the steps are collective) and sample the clocks under that load
-    need_probe = torch.tensor([1 if (rank == 0 and clk is not None and clk.get("samples") == 0 and
-                                     "nvidia-smi unavailable" not in clk.get("reasons", []) and
-                                     os.environ.get("MRI_BENCH_NO_CLOCKS") != "1") else 0], device=dev)
-    if world > 1:
-        dist.broadcast(need_probe, src=0)
-    if int(need_probe.item()):
-        probe = ClockSampler(local_rank)
-        if rank == 0:
-            probe.start()
-            time.sleep(0.4)
-        barrier()
-        probe.mark()
-        for i in range(total_steps, total_steps + max(20, int(500.0 / max(ms_step, 1e-3)))):
-            step(i)
-        barrier()
-        if rank == 0:
-            clk = probe.stop()
-            clk["window"] = "identical untimed steps run right after the timed region (it was shorter than one sample)"
-    value = n * world / (ms_step * 1e-3)
+    ms_step = max_over_ranks(ms) / steps
     final_loss = float(loss.detach())
+    # the same steps again for >= SUSTAIN_SECONDS (same count on every rank: the steps are collective), so that the clock
+    # samples describe the hardware state under this very load even when --steps is small
+    more = max(20, int(SUSTAIN_SECONDS * 1e3 / max(ms_step, 1e-3)) + 1)
+    ms2, _ = run_steps(warmup + steps, more)
+    sustained_ms_step = max_over_ranks(ms2) / more
+    clk = clocks.stop() if rank == 0 else None
+    if clk is not None:
+        clk["window"] = f"timed region ({steps} steps) + sustained window ({more} identical steps, {ms2 / 1e3:.2f} s)"
+    value = n * world / (ms_step * 1e-3)
+
+    # optimiser step as seen inside the training step (includes the gradient exchange at N > 1)
+    opt_ms = []
+    for i in range(12):
+        x, y = sampler.batch(index[i % ring])
+        model.training_step((x, y), i).backward()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); opt.step(); b.record()
+        opt.zero_grad()
+        barrier()
+        opt_ms.append(a.elapsed_time(b))
+    opt_step_ms = max_over_ranks(float(np.median(opt_ms[2:])))
 
     # ---- e2e: host batches through the public API (PrefetchLoader + LightningModule.training_step + FusedAdam)
     # every step: H2D copy of that step's batch from pinned host memory (overlapped with the previous step's
     # compute on a side stream) and a D2H read of that step's loss (async copy, consumed one step later).
-    host_ring = []
-    for r in range(4):
-        xb, yb = sampler.batch(index[r])
-        host_ring.append((xb.cpu().pin_memory(), yb.cpu().pin_memory()))
-    e2e_steps = max(10, min(args.steps, 100))
+    e2e_line = None
+    if e2e:
+        host_ring = []
+        for r in range(4):
+            xb, yb = sampler.batch(index[r])
+            host_ring.append((xb.cpu().pin_memory(), yb.cpu().pin_memory()))
+        e2e_steps = max(10, min(steps, 100))
 
-    class _HostBatches:
-        def __len__(self):
-            return e2e_steps + 3
+        class _HostBatches:
+            def __len__(self):
+                return e2e_steps + 3
 
-        def __iter__(self):
-            for i in range(len(self)):
-                yield host_ring[i % len(host_ring)]
+            def __iter__(self):
+                for i in range(len(self)):
+                    yield host_ring[i % len(host_ring)]
 
-    loss_host = torch.zeros(e2e_steps + 3, dtype=torch.float32).pin_memory()
-    loss_events = [torch.cuda.Event() for _ in range(e2e_steps + 3)]
-    losses = []
-    t0 = None
-    for i, (xb, yb) in enumerate(PrefetchLoader(_HostBatches(), dev) if not args.no_e2e else []):
-        if i == 3:  # 3 untimed warm-up steps
-            barrier()
-            t0 = time.perf_counter()
-        l = model.training_step((xb, yb), i)
-        l.backward()
-        opt.step()
-        opt.zero_grad()
-        loss_host[i].copy_(l.detach(), non_blocking=True)
-        loss_events[i].record()
-        if i >= 1:
-            loss_events[i - 1].synchronize()
-            losses.append(float(loss_host[i - 1]))
-    barrier()
-    if t0 is None:
-        t0 = time.perf_counter() - 1.0
-    e2e_dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = n * world / float(e2e_dt.item())
+        loss_host = torch.zeros(e2e_steps + 3, dtype=torch.float32).pin_memory()
+        loss_events = [torch.cuda.Event() for _ in range(e2e_steps + 3)]
+        losses = []
+        t0 = None
+        for i, (xb, yb) in enumerate(PrefetchLoader(_HostBatches(), dev)):
+            if i == 3:  # 3 untimed warm-up steps
+                barrier()
+                t0 = time.perf_counter()
+            l = model.training_step((xb, yb), i)
+            l.backward()
+            opt.step()
+            opt.zero_grad()
+            loss_host[i].copy_(l.detach(), non_blocking=True)
+            loss_events[i].record()
+            if i >= 1:
+                loss_events[i - 1].synchronize()
+                losses.append(float(loss_host[i - 1]))
+        barrier()
+        e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e_line = {"value": n * world / e2e_dt, "unit": "coords/s", "h2d_bytes_per_step": n * (dim + 1) * 4,
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps}
 
     # ---- inference: every rank sweeps its slab of the query volume (no communication), max over ranks
-    infer = None
-    if not args.no_infer:
+    infer_line = None
+    if infer:
         if is_hash:
-            sweep_shape = SWEEP_SHAPE if args.workload == "ankle_hash" else (256, 256, 256, 4)
+            sweep_shape = SWEEP_SHAPE if name == "ankle_hash" else (256, 256, 256, 4)
         else:
-            sweep_shape = (352, 352, 6, 29) if args.workload == "siren_ankle" else (256, 256, 128)
+            sweep_shape = (352, 352, 6, 29) if name == "siren_ankle" else (256, 256, 128)
         total_vox = int(np.prod(sweep_shape))
         ns = not is_hash
+        # everything that does not depend on the query (axis vectors, eval-mode BatchNorm folding, output buffers) is
+        # prepared once: the timed window holds the sweep kernels only
+        sweeper = sweep.SlabSweeper(model, sweep_shape, norm_siren=ns, rank=rank, world_size=world)
         for _ in range(2):
-            sweep.dense_sweep(model, sweep_shape, norm_siren=ns, rank=rank, world_size=world)
+            sweeper.run()
         barrier()
         reps, per_rep = 5, []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            out = sweep.dense_sweep(model, sweep_shape, norm_siren=ns, rank=rank, world_size=world)
+            sweeper.run()
             b.record()
             barrier()
             per_rep.append(a.elapsed_time(b))
         # median of the per-sweep device times: single sweeps occasionally stall for tens of ms on these shared boxes
-        sw = torch.tensor([float(np.median(per_rep))], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(sw, op=dist.ReduceOp.MAX)
-        sw_ms = float(sw.item())
-        t1 = time.perf_counter()
-        host = out.cpu()
-        d2h_s = time.perf_counter() - t1
-        infer = {"metric": "infer_voxels_per_s", "value": total_vox / (sw_ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
-                 "workload": f"dense sweep of {sweep_shape} ({total_vox} voxels), contiguous slab per GPU, "
-                             + ("fused hash+decoder kernel" if is_hash else "coordinate synthesis + tensor-core SIREN"),
-                 "ms": sw_ms, "ms_per_sweep": [round(v, 3) for v in per_rep],
-                 "e2e_value_with_d2h": total_vox / (sw_ms * 1e-3 + d2h_s)}
-        del host, out
+        sw_ms = max_over_ranks(float(np.median(per_rep)))
+        # end to end: the slab lands in pinned host memory, chunk by chunk, the copy of chunk i overlapping chunk i+1
+        sweeper.run_to_host()
+        barrier()
+        e2e_times = []
+        for _ in range(3):
+            t1 = time.perf_counter()
+            sweeper.run_to_host()
+            e2e_times.append(time.perf_counter() - t1)
+            barrier()
+        e2e_s = max_over_ranks(float(np.median(e2e_times)))
+        infer_line = {"metric": "infer_voxels_per_s", "value": total_vox / (sw_ms * 1e-3), "unit": "voxels/s", "n_gpus": world,
+                      "workload": f"dense sweep of {sweep_shape} ({total_vox} voxels), contiguous slab per GPU, "
+                                  + ("fused hash+decoder kernel, axis-0-fastest walk" if is_hash else "coordinate synthesis + tensor-core SIREN"),
+                      "ms": sw_ms, "ms_per_sweep": [round(v, 3) for v in per_rep],
+                      "e2e": {"value": total_vox / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": 0,
+                              "d2h_bytes_per_step": 4 * total_vox // world,
+                              "note": "slab copied to pinned host memory in chunks on a side stream while the next chunk computes"}}
+        del sweeper
 
     # ---- isolated kernel timings for the roofline (rank 0, L2 flushed between launches)
     roof, kern = None, None
-    if is_hash:
-        opt.disable_overlap(model.encoder)
-    opt.data_parallel = False  # the isolated-kernel section below runs on rank 0 only: no collectives in it
-    if rank == 0:
-        hbm_peak, peak_src = peaks()
+    if kernels:
+        if is_hash:
+            opt.disable_overlap(model.encoder)
+        opt.data_parallel = False  # the isolated-kernel section below runs on rank 0 only: no collectives in it
+    if kernels and rank == 0:
+        pk, peak_src = peaks()
+        hbm_peak = float(pk["hbm_gbs"])
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def timed(fn, reps=10):
@@ -515,7 +571,7 @@ def main():
                 fwd_ms = timed(lambda: enc(x))
             enc_out = enc(x)
             bwd_ms = timed(lambda: torch.autograd.backward(enc_out, go, retain_graph=True))
-            # the whole-model backward (ONE kernel when the decoder backward is fused with the scatter)
+            # the whole-model forward / backward (ONE kernel each when the decoder is fused with the gather / scatter)
             fused_ms = fused_fwd_ms = None
             if getattr(model, "fuse_backward", False):
                 pred = model(x)
@@ -539,7 +595,7 @@ def main():
                 "adam_step": {"ms": adam_ms, "GBps_algorithmic": adam_bytes / adam_ms / 1e6, "frac": adam_bytes / adam_ms / 1e6 / hbm_peak},
             }
             top = "hashgrid_bwd" if bwd_ms >= fwd_ms else "hashgrid_fwd"
-            traffic = 320.7e6 if top == "hashgrid_bwd" else 235.2e6
+            traffic = None
             if fused_ms is not None:
                 # fused decoder-backward + scatter: coords + enc + dy read, L*2^D*F*4 B reduced into the tables
                 fused_bytes = (HASH_BYTES_PER_COORD + 4) * n
@@ -547,15 +603,21 @@ def main():
                                            "frac": fused_bytes / fused_ms / 1e6 / hbm_peak}
                 kern["hashdecoder_fwd"] = {"ms": fused_fwd_ms, "GBps_algorithmic": (fused_bytes + 4 * n) / fused_fwd_ms / 1e6,
                                            "frac": (fused_bytes + 4 * n) / fused_fwd_ms / 1e6 / hbm_peak}
-                if fused_ms >= max(fwd_ms, bwd_ms):
-                    top, hash_bytes, traffic = "hashdecoder_bwd", fused_bytes, FUSED_BWD_DRAM_BYTES
+                top = "hashdecoder_bwd" if fused_ms >= fused_fwd_ms else "hashdecoder_fwd"
+                hash_bytes = fused_bytes if top == "hashdecoder_bwd" else fused_bytes + 4 * n
+                # ncu DRAM bytes were captured at 2^19 ankle-volume coords; other sizes / volumes have no capture
+                traffic = NCU_DRAM_BYTES[top] if (name == "ankle_hash" and batch_log2 == 19) else None
+            step_bytes = (2 * HASH_BYTES_PER_COORD + 8) * n + adam_bytes  # fused fwd + fused bwd + Adam, algorithmic
+            kern["whole_step"] = {"ms": ms_step, "algorithmic_GB": step_bytes / 1e9, "GBps_algorithmic": step_bytes / ms_step / 1e6,
+                                  "frac": step_bytes / ms_step / 1e6 / hbm_peak}
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[top]["frac"], "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": hash_bytes,
-                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x 2^19 coords (+4 B/coord dy for "
-                            "the fused decoder-backward+scatter kernel, which also does 8.4 kMAC/coord of decoder math); traffic "
-                            "= ncu dram read+write per launch (profiles/r01_ncu_full_hash_adam.csv): the 61 MB of tables stay "
-                            "in the 126 MB L2, the kernels are bound by the L1/L2 sector and L2 atomic rates, not HBM"}
+                    "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
+                    "peak_source": peak_src + " hbm_gbs", "algorithmic_bytes_per_launch": hash_bytes,
+                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x coords per launch (+4 B/coord dy "
+                            "for the fused decoder-backward+scatter kernel, which also does 8.4 kMAC/coord of decoder math); "
+                            "traffic = ncu dram read+write per launch: the 61 MB of tables stay in the 126 MB L2, so DRAM moves "
+                            "less than the algorithmic bytes - the kernels are bound by the L2 sector / L2 atomic rates "
+                            "(DESIGN.md 3), not HBM"}
         else:
             from mri_interpolation_b200 import tc
             from mri_interpolation_b200._lib import ACT_SINE
@@ -568,41 +630,85 @@ def main():
             ms_l = timed(lambda: tc.layer(a_hi, a_lo, w_hi, w_lo, bias, ACT_SINE, 30.0, passes=3, want_planes=True, want_aux=True), reps=5)
             gw = torch.zeros(h, h, device=dev)
             ms_w = timed(lambda: tc.wgrad(a_hi, a_lo, a_hi, a_lo, gw, None, passes=3), reps=5)
-            tf_peak = 1649.2
-            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.isfile(pk):
-                tf_peak = float(json.load(open(pk))["bf16_tflops"])
+            tf_burst, tf_sust = float(pk["bf16_tflops"]), float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"]))
             issued = 3 * 2.0 * n * h * h
-            kern = {"siren_tc_layer_fwd": {"ms": ms_l, "issued_bf16_TFLOPs": issued / ms_l / 1e9, "frac": issued / ms_l / 1e9 / tf_peak},
-                    "siren_tc_wgrad": {"ms": ms_w, "issued_bf16_TFLOPs": issued / ms_w / 1e9, "frac": issued / ms_w / 1e9 / tf_peak}}
+            kern = {"siren_tc_layer_fwd": {"ms": ms_l, "issued_bf16_TFLOPs": issued / ms_l / 1e9, "frac": issued / ms_l / 1e9 / tf_burst},
+                    "siren_tc_wgrad": {"ms": ms_w, "issued_bf16_TFLOPs": issued / ms_w / 1e9, "frac": issued / ms_w / 1e9 / tf_burst}}
             roof = {"kernel": "siren_tc_layer_kernel (hidden layer forward, bf16x3 split precision, sine epilogue)",
-                    "bound": "tensor", "achieved": kern["siren_tc_layer_fwd"]["issued_bf16_TFLOPs"], "peak": tf_peak,
+                    "bound": "tensor", "achieved": kern["siren_tc_layer_fwd"]["issued_bf16_TFLOPs"], "peak": tf_burst,
                     "unit": "TFLOP/s", "frac": kern["siren_tc_layer_fwd"]["frac"], "traffic": None,
-                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)",
+                    "peak_source": peak_src + " bf16_tflops (burst: the kernel is timed alone)",
                     "algorithmic_flops_per_launch": 2.0 * n * h * h,
                     "note": "issued = 3 tcgen05.mma passes x 2 n H^2 (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi); the fp32-equivalent "
                             "(algorithmic) rate is one third of it"}
             if info.get("train_flops_per_coord"):
-                kern["whole_step_algorithmic_TFLOPs"] = info["train_flops_per_coord"] * n / (ms_step * 1e-3) / 1e12
+                alg = info["train_flops_per_coord"] * n / (ms_step * 1e-3) / 1e12
+                kern["whole_step"] = {"ms": ms_step, "algorithmic_TFLOPs": alg, "issued_bf16_TFLOPs": 3 * alg,
+                                      "frac_of_sustained_peak": 3 * alg / tf_sust,
+                                      "note": "in-step figure against bf16_tflops_sustained (a long step runs under the power cap)"}
+        del flush
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline and args.workload == "ankle_hash":
-        v, dt, ncpu = time_oracle(args.cpu_batch_log2, 3, 1)
-        cpu = {"value": v, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"3 steps of 2^{args.cpu_batch_log2} coords of the same training step (oracle port of the "
-                         f"reference's PyTorch CPU path), {dt * 1e3:.0f} ms/step"}
-
+    line = None
     if rank == 0:
         line = {
-            "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "train_coords_per_s", "value": value, "unit": "coords/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if is_hash else "f32 via bf16x3 split on tcgen05 (fp32 accumulate)",
-            "data": info["data"], "config": workload_config(args), "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": "coords/s", "h2d_bytes_per_step": n * (dim + 1) * 4, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps},
-            "gpu_launches": launches, "final_loss": final_loss, "sampler_ms_per_batch": sampler_ms,
-            "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "infer": infer,
+            "data": info["data"], "config": workload_config(args, name, batch_log2, world), "clocks": clk,
+            "sustained": {"steps": more, "ms_per_step": sustained_ms_step, "value": n * world / (sustained_ms_step * 1e-3)},
+            "e2e": e2e_line, "gpu_launches": launches, "final_loss": final_loss,
+            "sampler_ms_per_batch": sampler_ms, "sampler": sampler_how,
+            "optimizer_step_ms": opt_step_ms,
+            "roofline": roof, "kernels": kern, "infer": infer_line,
         }
+        if kern and "adam_step" in kern:
+            # what the gradient exchange adds to the optimiser step: in-step optimiser time minus the single-GPU Adam kernel
+            line["exchange_exposed_ms"] = max(0.0, opt_step_ms - kern["adam_step"]["ms"]) if world > 1 else 0.0
+    del model, opt, sampler, index
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from mri_interpolation_b200 import distributed
+
+    # the CPU baseline runs BEFORE the process group exists (rank 0 of a single-GPU run only: under torchrun the other
+    # ranks would spin in a barrier on the same host cores and contaminate it - round-1 finding)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu = None
+    if world_env == 1 and not args.no_cpu_baseline and args.workload == "ankle_hash":
+        v, dt, ncpu, kind = time_reference(args.cpu_batch_log2, 2, 1)
+        cpu = {"value": v, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": kind,
+               "sample": cpu_sample_text(kind, 2, args.cpu_batch_log2, dt)}
+
+    rank, local_rank, world = distributed.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    import torch.distributed as dist
+
+    line = run_leg(args, args.workload, args.batch_log2, args.steps, args.warmup, dev, rank, local_rank, world,
+                   e2e=not args.no_e2e, infer=not args.no_infer, kernels=True)
+    extra = {}
+    if not args.no_workloads and args.workload == "ankle_hash":
+        for name in EXTRA_LEGS:
+            steps = 20 if name == "siren_wide" else 40
+            leg = run_leg(args, name, WORKLOADS[name][1], steps, 3, dev, rank, local_rank, world,
+                          e2e=False, infer=(name != "synthetic_hash"), kernels=True)
+            if rank == 0:
+                extra[name] = {k: leg[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "dtype", "data",
+                                                   "config", "clocks", "sustained", "gpu_launches", "final_loss", "roofline", "kernels",
+                                                   "infer", "optimizer_step_ms", "sampler_ms_per_batch")}
+    if rank == 0:
+        line["cpu_baseline"] = cpu
+        if extra:
+            line["workloads"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -29,6 +29,7 @@ struct BatchCoords {
     load_coord<D>(x, r_lo < n ? r_lo : 0, lo);
     load_coord<D>(x, r_hi < n ? r_hi : 0, hi);
   }
+  __device__ __forceinline__ int64_t out_index(int64_t row) const { return row; }
 };
 // ... or synthesised from the flat voxel index of a dense grid: lanes 0-15 each decompose one index, the quads pick
 // their two rows up with shuffles (no 4x redundant integer divisions)
@@ -47,6 +48,52 @@ struct SweepCoords {
       lo[d] = __shfl_sync(0xffffffffu, v[d], g);
       hi[d] = __shfl_sync(0xffffffffu, v[d], g + 8);
     }
+  }
+  __device__ __forceinline__ int64_t out_index(int64_t row) const { return row; }
+};
+// ... or from a whole-plane box [plane0, plane0 + planes) x (other axes) of the grid walked with the axis-0 index
+// FASTEST (then axis 1, 2, 3): axis 0 is the one axis whose hash prime is 1, so the 16 voxels of an m-tile - neighbours
+// along axis 0 - gather from neighbouring table rows (same 128-byte lines / 32-byte sectors on all but the finest
+// levels), where a C-order walk (last axis fastest) lands every voxel on unrelated rows.  The result is stored at the
+// voxel's C-order position, so the output volume is the same array.
+template <int D>
+struct SweepCoordsAxis0 {
+  const float* axes;
+  GridDesc gd;
+  int64_t out_base;   // C-order index of the box's first voxel minus the C-order index out[0] stands for
+  uint32_t plane0, planes;
+  __device__ __forceinline__ void decompose(uint32_t r, uint32_t (&i)[D]) const {
+    uint32_t q = r / planes;
+    i[0] = plane0 + (r - q * planes);
+#pragma unroll
+    for (int d = 1; d < D - 1; ++d) {
+      const uint32_t q2 = q / static_cast<uint32_t>(gd.shape[d]);
+      i[d] = q - q2 * static_cast<uint32_t>(gd.shape[d]);
+      q = q2;
+    }
+    i[D - 1] = q;
+  }
+  __device__ __forceinline__ void load_pair(int64_t row0, int64_t n, int lane, float (&lo)[D], float (&hi)[D]) const {
+    const int64_t r = row0 + (lane & 15);
+    uint32_t i[D];
+    decompose(static_cast<uint32_t>(r < n ? r : 0), i);
+    float v[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = __ldg(axes + gd.axis_off[d] + i[d]);
+    const int g = lane >> 2;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      lo[d] = __shfl_sync(0xffffffffu, v[d], g);
+      hi[d] = __shfl_sync(0xffffffffu, v[d], g + 8);
+    }
+  }
+  __device__ __forceinline__ int64_t out_index(int64_t row) const {
+    uint32_t i[D];
+    decompose(static_cast<uint32_t>(row), i);
+    int64_t flat = i[0] - plane0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) flat = flat * gd.shape[d] + i[d];
+    return out_base + flat;
   }
 };
 
@@ -123,8 +170,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 3) hashdecoder_mma_fwd_kernel(con
     s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
     s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
     if (t == 0) {
-      if (rows[0] < n) { const float p = s_lo + b2v; y[rows[0]] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[rows[0]] = p; }
-      if (rows[1] < n) { const float p = s_hi + b2v; y[rows[1]] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[rows[1]] = p; }
+      if (rows[0] < n) { const float p = s_lo + b2v; const int64_t o = src.out_index(rows[0]); y[o] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[o] = p; }
+      if (rows[1] < n) { const float p = s_hi + b2v; const int64_t o = src.out_index(rows[1]); y[o] = activate_rt(act2, p, 1.0f); if (pre2_out) pre2_out[o] = p; }
     }
   }
 }
@@ -165,12 +212,44 @@ int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int64_t fir
                      const LevelTable& T, const float* decoder, int act, int last_act, float* out, cudaStream_t s) {
   constexpr int K0 = 32, H = 64;  // packed decoder: W1 (H x K0), b1 (H), w2 (H), b2 (1)
   const float *w1 = decoder, *b1 = decoder + H * K0, *w2 = b1 + H, *b2 = w2 + H;
-#define CALL(DV, ACTV)                                                                                              \
-  launch_fused_fwd<DV, ACTV>(SweepCoords<DV>{axes, gd, first}, count, tables, T, w1, b1, w2, b2, last_act, nullptr, out, \
+  // whole axis-0 planes inside [first, first + count) are walked axis-0-fastest; a ragged head / tail (slab boundaries
+  // that cut a plane) keeps the C-order walk.  MRI_SWEEP_ORDER=c restores the C-order walk everywhere (A/B runs).
+  static const bool axis0_walk = [] { const char* e = getenv("MRI_SWEEP_ORDER"); return !(e && e[0] == 'c'); }();
+  int64_t plane = 1;
+  for (int d = 1; d < dim; ++d) plane *= gd.shape[d];
+  const int64_t p_begin = (first + plane - 1) / plane, p_end = (first + count) / plane;
+  const bool boxed = axis0_walk && p_end > p_begin && (p_end - p_begin) * plane < (int64_t{1} << 32);
+  const int64_t head = boxed ? p_begin * plane - first : count;
+  const int64_t box = boxed ? (p_end - p_begin) * plane : 0;
+  const int64_t tail = count - head - box;
+#define CALL_C(DV, ACTV, FIRST, COUNT, OUT)                                                                              \
+  launch_fused_fwd<DV, ACTV>(SweepCoords<DV>{axes, gd, FIRST}, COUNT, tables, T, w1, b1, w2, b2, last_act, nullptr, OUT, \
                              nullptr, s)
-  if (dim == 3) return act == MRI_ACT_GELU ? CALL(3, MRI_ACT_GELU) : CALL(3, MRI_ACT_RELU);
-  return act == MRI_ACT_GELU ? CALL(4, MRI_ACT_GELU) : CALL(4, MRI_ACT_RELU);
-#undef CALL
+#define CALL_B(DV, ACTV)                                                                                                          \
+  launch_fused_fwd<DV, ACTV>(SweepCoordsAxis0<DV>{axes, gd, head, static_cast<uint32_t>(p_begin), static_cast<uint32_t>(p_end - p_begin)}, \
+                             box, tables, T, w1, b1, w2, b2, last_act, nullptr, out, nullptr, s)
+#define RUN(CALLEXPR)                              \
+  do {                                             \
+    const int st_ = (CALLEXPR);                    \
+    if (st_ != MRI_OK) return st_;                 \
+  } while (0)
+#define DISPATCH(DV, ACTV)                                                              \
+  do {                                                                                  \
+    if (head > 0) RUN(CALL_C(DV, ACTV, first, head, out));                              \
+    if (box > 0) RUN(CALL_B(DV, ACTV));                                                 \
+    if (tail > 0) RUN(CALL_C(DV, ACTV, first + head + box, tail, out + head + box));    \
+    return MRI_OK;                                                                      \
+  } while (0)
+  if (dim == 3) {
+    if (act == MRI_ACT_GELU) DISPATCH(3, MRI_ACT_GELU);
+    DISPATCH(3, MRI_ACT_RELU);
+  }
+  if (act == MRI_ACT_GELU) DISPATCH(4, MRI_ACT_GELU);
+  DISPATCH(4, MRI_ACT_RELU);
+#undef DISPATCH
+#undef RUN
+#undef CALL_B
+#undef CALL_C
 }
 
 }  // namespace mri

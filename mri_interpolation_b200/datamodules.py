@@ -31,59 +31,50 @@ def create_mgrid(shape: Sequence[int]) -> torch.Tensor:
     return torch.stack(torch.meshgrid(*mgrid_axes(shape), indexing="ij"), dim=-1)
 
 
-class DeviceBatchLoader:
-    """Iterable of (coords, pixels) batches cut from tensors that already live on `device`.
+class ShuffledEpochs:
+    """Index stream of shuffled epochs over ``n`` samples: ``epoch()`` returns this rank's sample indices of one epoch,
+    batch after batch.  A batch is the set of samples at positions [i*B, (i+1)*B) of a fresh device-side permutation,
+    exactly as with the reference's shuffled DataLoader.
 
-    ``shuffle=True`` draws a fresh permutation per epoch from ``generator`` (device-side randperm); a batch is the set of
-    voxels at positions [i*B, (i+1)*B) of that permutation, exactly as with the reference's shuffled DataLoader.
     ``rank``/``world_size`` give each data-parallel rank a disjoint strided share of every epoch; the permutation is
     padded (wrapping around, like ``DistributedSampler``) to a multiple of ``world_size`` so that every rank sees the
     SAME number of batches of the SAME sizes - the optimiser step is collective, a rank with one batch more would hang.
 
-    ``grid_shape`` (the C-order voxel grid the rows of ``coords`` enumerate) switches on *locality-ordered batches*:
-    inside a batch the samples are arranged with the axis-0 index running fastest (functional.locality_key).  The batch
-    SET is unchanged and the loss is a mean over the batch, so training is the same up to fp32 summation order, but
+    ``grid_shape`` (the C-order voxel grid the samples enumerate) switches on *locality-ordered batches*: inside a batch
+    the samples are arranged with the axis-0 index running fastest (functional.locality_key).  The batch SET is
+    unchanged and the loss is a mean over the batch, so training is the same up to fp32 summation order, but
     neighbouring rows of a batch now hit neighbouring hash-table rows: -32 % L2 sectors in the gather, and the scatter
-    can merge duplicate updates (csrc/hash_device.cuh).  One stable sort of small keys per epoch pays for it:
-    voxels are kept in locality order once, and an epoch's permutation is turned into (batch id per voxel) and
-    stably sorted by that id.
+    can merge duplicate updates (csrc/hash_device.cuh).  It costs one stable sort of small keys per epoch: the voxels
+    are kept in locality order once, an epoch's permutation is turned into (batch id per voxel) and stably sorted by
+    that id (measured on B200, 11.15 M voxels: 2.2 ms per epoch against 1.1 ms for torch.randperm alone).
     """
 
-    def __init__(self, coords: torch.Tensor, pixels: torch.Tensor, batch_size: int, shuffle: bool = False,
-                 device: Optional[torch.device] = None, seed: int = 1337, rank: int = 0, world_size: int = 1,
-                 drop_last: bool = False, grid_shape: Optional[Sequence[int]] = None, locality: bool = True):
-        self.device = torch.device(device) if device is not None else coords.device
-        self.coords = coords.to(self.device)
-        self.pixels = pixels.to(self.device)
-        self.batch_size = int(batch_size)
-        self.shuffle = shuffle
+    def __init__(self, n: int, batch_size: int, device, seed: int = 1337, rank: int = 0, world_size: int = 1,
+                 grid_shape: Optional[Sequence[int]] = None, locality: bool = True):
+        self.n, self.batch_size = int(n), int(batch_size)
+        self.device = torch.device(device)
         self.rank, self.world_size = rank, world_size
-        self.drop_last = drop_last
-        self.dataset = torch.utils.data.TensorDataset(self.coords, self.pixels)
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(seed)
-        self.epoch = 0
         self._loc_order = None
-        if grid_shape is not None and locality and shuffle:
-            if int(np.prod(grid_shape)) != self.coords.shape[0]:
-                raise ValueError(f"grid_shape {tuple(grid_shape)} does not enumerate the {self.coords.shape[0]} rows of coords")
+        if grid_shape is not None and locality:
+            if int(np.prod(grid_shape)) != self.n:
+                raise ValueError(f"grid_shape {tuple(grid_shape)} does not enumerate {self.n} samples")
             from .functional import locality_key
-            flat = torch.arange(self.coords.shape[0], device=self.device)
+            flat = torch.arange(self.n, device=self.device)
             self._loc_order = torch.argsort(locality_key(flat, grid_shape, block=1))
 
-    def _local_count(self) -> int:
-        n = self.coords.shape[0]
-        return (n + self.world_size - 1) // self.world_size
+    def local_count(self) -> int:
+        return (self.n + self.world_size - 1) // self.world_size
 
-    def __len__(self) -> int:
-        n = self._local_count()
-        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+    def batches_per_epoch(self, drop_last: bool = False) -> int:
+        m = self.local_count()
+        return m // self.batch_size if drop_last else (m + self.batch_size - 1) // self.batch_size
 
-    def epoch_indices(self) -> torch.Tensor:
-        """This rank's sample indices of one shuffled epoch, batch after batch (advances the generator)."""
-        n, w, b = self.coords.shape[0], self.world_size, self.batch_size
+    def epoch(self) -> torch.Tensor:
+        n, w, b = self.n, self.world_size, self.batch_size
         perm = torch.randperm(n, device=self.device, generator=self._gen)  # perm[p] = voxel at position p
-        total = self._local_count() * w
+        total = self.local_count() * w
         if total > n:
             perm = torch.cat([perm, perm[: total - n]])
         if self._loc_order is None:
@@ -105,14 +96,46 @@ class DeviceBatchLoader:
         if w > 1:
             mine = (p % w) == self.rank
             vox, p = vox[mine], p[mine] // w
-        batch_id = (p // b).to(torch.int32)
-        _, order = torch.sort(batch_id, stable=True)   # few distinct keys; voxels stay in locality order inside a batch
+        batch_id = p // b
+        n_batches = (self.local_count() + b - 1) // b
+        batch_id = batch_id.to(torch.uint8 if n_batches <= 255 else torch.int16 if n_batches <= 32767 else torch.int32)
+        _, order = torch.sort(batch_id, stable=True)   # few key bits; voxels stay in locality order inside a batch
         return vox[order]
 
+
+class DeviceBatchLoader:
+    """Iterable of (coords, pixels) batches cut from tensors that already live on `device`.
+
+    ``shuffle=True`` draws a fresh permutation per epoch (`ShuffledEpochs`: same batch sets as the reference's shuffled
+    DataLoader, equal batch counts and sizes on every data-parallel rank); with ``grid_shape`` - the C-order voxel grid
+    the rows of ``coords`` enumerate - the samples of a batch are arranged in locality order (axis-0 index fastest).
+    """
+
+    def __init__(self, coords: torch.Tensor, pixels: torch.Tensor, batch_size: int, shuffle: bool = False,
+                 device: Optional[torch.device] = None, seed: int = 1337, rank: int = 0, world_size: int = 1,
+                 drop_last: bool = False, grid_shape: Optional[Sequence[int]] = None, locality: bool = True):
+        self.device = torch.device(device) if device is not None else coords.device
+        self.coords = coords.to(self.device)
+        self.pixels = pixels.to(self.device)
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        self.rank, self.world_size = rank, world_size
+        self.drop_last = drop_last
+        self.dataset = torch.utils.data.TensorDataset(self.coords, self.pixels)
+        self.epoch = 0
+        self.epochs = ShuffledEpochs(self.coords.shape[0], self.batch_size, self.device, seed, rank, world_size,
+                                     grid_shape if shuffle else None, locality)
+
+    def __len__(self) -> int:
+        return self.epochs.batches_per_epoch(self.drop_last)
+
+    def epoch_indices(self) -> torch.Tensor:
+        """This rank's sample indices of one shuffled epoch, batch after batch (advances the generator)."""
+        return self.epochs.epoch()
+
     def __iter__(self):
-        n = self.coords.shape[0]
         if self.shuffle:
-            order = self.epoch_indices()
+            order = self.epochs.epoch()
             for i in range(len(self)):
                 idx = order[i * self.batch_size:(i + 1) * self.batch_size]
                 yield self.coords.index_select(0, idx), self.pixels.index_select(0, idx)
