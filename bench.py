@@ -686,6 +686,9 @@ def main():
         cpu = {"value": v, "unit": "coords/s", "cores": torch.get_num_threads(), "kind": kind,
                "sample": cpu_sample_text(kind, 2, args.cpu_batch_log2, dt)}
 
+    # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT, in front of the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = distributed.init_from_env("nccl")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")

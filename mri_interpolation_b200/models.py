@@ -413,8 +413,8 @@ class HashMLP(BaseMLP):
 
 
 class _OutOfScope(pl.LightningModule):
-    """Reference model-zoo variants that are not on the north-star hot path: the
-    names stay importable because config/base.py imports them, but they are not implemented."""
+    """Reference model-zoo variants that are not on the north-star hot path (point-spread-function, random
+    Fourier feature and Gabor experiments; rff / PSF helpers are absent): the names stay importable, construction raises."""
 
     def __init__(self, *args, **kwargs):
         raise NotImplementedError(
@@ -422,14 +422,14 @@ class _OutOfScope(pl.LightningModule):
             f"Adam); see DESIGN.md 'Out of scope'")
 
 
-class Modulator(_OutOfScope): ...
-class ModulatedSirenNet(_OutOfScope): ...
-class HashSirenNet(_OutOfScope): ...
 class PsfSirenNet(_OutOfScope): ...
 class RffNet(_OutOfScope): ...
-class TcnnHashMLP(_OutOfScope): ...
 class RealGaborLayer(_OutOfScope): ...
 class ComplexGaborLayer(_OutOfScope): ...
 class GaborNet(_OutOfScope): ...
-class MultiSiren(_OutOfScope): ...
-class MultiHashMLP(_OutOfScope): ...
+
+
+# the model-zoo variants that sit on the hot-path operators (modulated SIRENs, tiny-cuda-nn shaped front-ends) live in
+# zoo.py; imported last because zoo.py builds on the classes above
+from .zoo import (HashSirenNet, ModulatedSirenNet, Modulator, MultiHashMLP, MultiSiren, TcnnHashMLP,  # noqa: E402,F401
+                  TcnnStyleEncoding, TcnnStyleNetwork)

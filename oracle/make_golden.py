@@ -268,6 +268,40 @@ def golden_hashmlp(ref_models):
     print(f"hashmlp: loss={float(loss):.6f} bn_loss={float(loss_bn):.6f}")
 
 
+def golden_zoo(ref_models):
+    """Model-zoo variants on the hot-path operators: fixtures straight from the reference's classes
+    (ModulatedSirenNet models.py:263-322, MultiSiren :888-956); the tcnn-backed classes cannot run in the reference."""
+    kw = dict(dim_in=3, dim_hidden=32, dim_out=1, n_layers=3, w0=30.0, w0_initial=30.0)
+    torch.manual_seed(1337)
+    ref = ref_models.ModulatedSirenNet(**kw)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(83, 3, generator=gen) * 2 - 1
+    y = torch.rand(83, 1, generator=gen)
+    pred = ref(x.clone())
+    loss = torch.nn.functional.mse_loss(y, pred)
+    loss.backward()
+    fx = dict(x=x.numpy(), y=y.numpy(), pred=pred.detach().numpy(), loss=float(loss), **{f"kw_{k}": v for k, v in kw.items()})
+    for k, p in ref.named_parameters():
+        fx[f"param:{k}"] = p.detach().numpy()
+        if p.grad is not None:
+            fx[f"grad:{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "modulated_siren_small.npz"), **fx)
+    print(f"modulated siren: loss={float(loss):.6f}")
+    torch.manual_seed(1337)
+    ms = ref_models.MultiSiren(dim_in=3, dim_hidden=16, dim_out=1, n_layers=2, n_frames=3, lr=1e-4)
+    xf = torch.rand(1, 40, 3, generator=gen) * 2 - 1
+    yf = torch.rand(1, 40, 1, generator=gen)
+    loss = ms.training_step((xf, yf, 2), 0)
+    loss.backward()
+    fx = dict(x=xf.numpy(), y=yf.numpy(), loss=float(loss), pred=ms(xf[0], 2).detach().numpy())
+    for k, p in ms.named_parameters():
+        fx[f"param:{k}"] = p.detach().numpy()
+        if p.grad is not None:
+            fx[f"grad:{k}"] = p.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "multi_siren_small.npz"), **fx)
+    print(f"multi siren: loss={float(loss):.6f}")
+
+
 def golden_adam():
     gen = torch.Generator().manual_seed(11)
     for name, kw in (("default", dict(lr=5e-3)), ("tcnn_like", dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-15)),
@@ -314,6 +348,7 @@ def main():
     golden_hash(ref_encoding)
     golden_siren(ref_models)
     golden_hashmlp(ref_models)
+    golden_zoo(ref_models)
     golden_adam()
     golden_sweep()
     print("oracle pinned against the reference; fixtures in", GOLD)

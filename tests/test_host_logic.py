@@ -90,7 +90,11 @@ def test_fast_hash_utility_matches_oracle():
 
 
 def test_out_of_scope_names_importable_but_not_constructible():
-    for name in ("HashSirenNet", "ModulatedSirenNet", "MultiHashMLP", "MultiSiren", "RffNet", "GaborNet"):
+    # config/base.py:12-14 imports these six names; the first four are implemented (zoo.py, tests/test_zoo.py), the
+    # PSF / random-Fourier-feature / Gabor experiments stay importable stubs
+    for name in ("HashSirenNet", "ModulatedSirenNet", "MultiHashMLP", "MultiSiren", "SirenNet", "HashMLP"):
+        assert isinstance(getattr(models, name), type)
+    for name in ("RffNet", "GaborNet", "PsfSirenNet", "RealGaborLayer", "ComplexGaborLayer"):
         with pytest.raises(NotImplementedError):
             getattr(models, name)()
 
