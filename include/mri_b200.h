@@ -79,6 +79,13 @@ int mri_hashgrid_backward_levels(const float* x, int64_t n, int dim, const float
                                  float* grad_tables, const mri_level_t* host_levels, int n_levels,
                                  int n_features, int level_begin, int level_count, void* stream);
 
+/* mri_hashgrid_forward run through the SAME gather code with the addressed table row of every corner also stored:
+ * rows_out (n, L, 2^dim) uint32 in the reference's corner order (bit d of the corner number = upper cell on axis d,
+ * encoding.py:101-106).  Parity instrumentation: the indices asserted bit-exact are those of the path that ships. */
+int mri_hashgrid_forward_rows(const float* x, int64_t n, int dim, const float* tables,
+                              const mri_level_t* host_levels, int n_levels, int n_features,
+                              float* out, uint32_t* rows_out, void* stream);
+
 /* Parity probe: corner hashes (n, L, 2^dim) uint32 and weights (n, L, 2^dim) f32 in the
  * reference's corner order (encoding.py:69-78, 101-106, 121-124). Either output may be NULL. */
 int mri_hashgrid_corners(const float* x, int64_t n, int dim, const mri_level_t* host_levels,

@@ -43,6 +43,7 @@ _D = ctypes.c_double
 # name -> argtypes; every function returns int (status) unless listed in _SPECIAL
 SIGNATURES = {
     "mri_hashgrid_forward": [_P, _I64, _I, _P, ctypes.POINTER(Level), _I, _I, _P, _P],
+    "mri_hashgrid_forward_rows": [_P, _I64, _I, _P, ctypes.POINTER(Level), _I, _I, _P, _P, _P],
     "mri_hashgrid_backward": [_P, _I64, _I, _P, _P, ctypes.POINTER(Level), _I, _I, _P],
     "mri_hashgrid_backward_levels": [_P, _I64, _I, _P, _P, ctypes.POINTER(Level), _I, _I, _I, _I, _P],
     "mri_hashgrid_corners": [_P, _I64, _I, ctypes.POINTER(Level), _I, _P, _P, _P],

@@ -60,9 +60,11 @@ __device__ __forceinline__ void store_feat(float* dst, const Feat<F>& a) {
 // pair hash to rows h and h' = h ^ (x0 ^ (x0+1)); for x0 % 4 != 3 they fall into the same 32-byte sector
 // (F = 2: 8-byte rows), and because they now sit in neighbouring lanes of the SAME load/red instruction the
 // LSU merges them into one L1 wavefront / one L2 request: ~10 instead of 16 sectors per (coordinate, level).
+// `row_sink` (parity instrumentation, nullptr in every production launch and then compiled away): the table row each
+// gather of THIS code path addresses, stored at the reference's corner number (bit d = upper cell on axis d).
 template <int D, int F, bool POW2>
 __device__ __forceinline__ Feat<F> encode_half_level(const Cell<D>& cell, int b0, const LevelDev& lv,
-                                                     const float* __restrict__ tbl) {
+                                                     const float* __restrict__ tbl, uint32_t* row_sink = nullptr) {
   constexpr int CH = 1 << (D - 1);
   const uint32_t t0 = cell.lo[0] + static_cast<uint32_t>(b0);
   const float w0 = b0 ? cell.wu[0] : cell.wl[0];
@@ -72,7 +74,9 @@ __device__ __forceinline__ Feat<F> encode_half_level(const Cell<D>& cell, int b0
     uint32_t h = t0;
 #pragma unroll
     for (int d = 1; d < D; ++d) h ^= ((c >> (d - 1)) & 1) ? (cell.lo[d] + prime(d)) : cell.lo[d];
-    rows[c] = gather_row<F>(tbl + static_cast<size_t>(wrap_rows<POW2>(h, lv)) * F);
+    const uint32_t row = wrap_rows<POW2>(h, lv);
+    if (row_sink != nullptr) row_sink[b0 | (c << 1)] = row;
+    rows[c] = gather_row<F>(tbl + static_cast<size_t>(row) * F);
   }
   Feat<F> acc;
 #pragma unroll

@@ -16,10 +16,13 @@ namespace mri {
 
 namespace {
 
-template <int D, int F>
+// SINK = true is the same kernel with the row of every gather also written out (mri_hashgrid_forward_rows: the parity
+// tests assert the indices of the path that ships, not of a separate probe); SINK = false compiles the sink away.
+template <int D, int F, bool SINK = false>
 __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const float* __restrict__ x, const float* __restrict__ tables,
                                                            const __grid_constant__ LevelTable T, int64_t n,
-                                                           int out_stride, float* __restrict__ out) {
+                                                           int out_stride, float* __restrict__ out,
+                                                           uint32_t* __restrict__ rows_out = nullptr) {
   const int level = blockIdx.y;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 128 + (threadIdx.x >> 1);
   const int b0 = threadIdx.x & 1;
@@ -29,7 +32,9 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const float* __restri
   load_coord<D>(x, live ? i : 0, xv);
   const Cell<D> cell = make_cell<D>(xv, lv);
   const float* __restrict__ tbl = tables + lv.offset;
-  Feat<F> acc = lv.is_pow2 ? encode_half_level<D, F, true>(cell, b0, lv, tbl) : encode_half_level<D, F, false>(cell, b0, lv, tbl);
+  uint32_t* sink = nullptr;
+  if constexpr (SINK) sink = live ? rows_out + (i * gridDim.y + level) * (1 << D) : nullptr;
+  Feat<F> acc = lv.is_pow2 ? encode_half_level<D, F, true>(cell, b0, lv, tbl, sink) : encode_half_level<D, F, false>(cell, b0, lv, tbl, sink);
 #pragma unroll
   for (int f = 0; f < F; ++f) acc.v[f] += __shfl_xor_sync(0xffffffffu, acc.v[f], 1);
   if (live && b0 == 0) store_feat<F>(out + i * out_stride + level * F, acc);
@@ -80,6 +85,14 @@ int launch_fwd(const float* x, const float* tables, const LevelTable& T, int64_t
   dim3 grid(static_cast<unsigned>((n + 127) / 128), n_levels);  // 2 lanes per coordinate
   hashgrid_fwd_kernel<D, F><<<grid, 256, 0, s>>>(x, tables, T, n, n_levels * F, out);
   MRI_LAUNCH_OK("hashgrid_fwd_kernel");
+  return MRI_OK;
+}
+template <int D, int F>
+int launch_fwd_rows(const float* x, const float* tables, const LevelTable& T, int64_t n, int n_levels, float* out,
+                    uint32_t* rows_out, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((n + 127) / 128), n_levels);
+  hashgrid_fwd_kernel<D, F, true><<<grid, 256, 0, s>>>(x, tables, T, n, n_levels * F, out, rows_out);
+  MRI_LAUNCH_OK("hashgrid_fwd_kernel<rows>");
   return MRI_OK;
 }
 template <int D, int F>
@@ -161,6 +174,27 @@ extern "C" int mri_hashgrid_forward(const float* x, int64_t n, int dim, const fl
   if (st != MRI_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define CALL(D, F) launch_fwd<D, F>(x, tables, T, n, n_levels, out, s)
+  MRI_DISPATCH_DF(dim, n_features, CALL)
+#undef CALL
+}
+
+extern "C" int mri_hashgrid_forward_rows(const float* x, int64_t n, int dim, const float* tables,
+                                         const mri_level_t* host_levels, int n_levels, int n_features, float* out,
+                                         uint32_t* rows_out, void* stream) {
+  int st = check_common(x, n, dim, host_levels, n_levels, n_features);
+  if (st != MRI_OK) return st;
+  if (n == 0) return MRI_OK;
+  if (!tables || !out || !rows_out) return fail(MRI_ERR_INVALID, "hashgrid_forward_rows: null tables/out/rows_out");
+  if ((reinterpret_cast<uintptr_t>(tables) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(MRI_ERR_INVALID, "hashgrid_forward_rows: tables/out must be 16-byte aligned");
+  for (int l = 0; l < n_levels; ++l)
+    if (host_levels[l].offset % (n_features >= 4 ? 4 : n_features))
+      return fail(MRI_ERR_INVALID, "hashgrid_forward_rows: level %d offset not aligned to the feature vector", l);
+  LevelTable T;
+  st = make_level_table(host_levels, n_levels, dim, &T);
+  if (st != MRI_OK) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define CALL(D, F) launch_fwd_rows<D, F>(x, tables, T, n, n_levels, out, rows_out, s)
   MRI_DISPATCH_DF(dim, n_features, CALL)
 #undef CALL
 }

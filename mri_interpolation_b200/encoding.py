@@ -137,6 +137,11 @@ class _MultiResBase(_GridKernelMixin):
         """(n, L, 2^D) hashes and weights straight from the CUDA kernel (parity probe)."""
         return Fn.hashgrid_corners(x, self)
 
+    @torch.no_grad()
+    def gathered_rows(self, x: torch.Tensor):
+        """(encoding, (n, L, 2^D) table rows) from the production gather kernel itself (not the probe)."""
+        return Fn.hashgrid_forward_rows(x, self)
+
 
 class MultiResHashGrid(_MultiResBase, nn.Module):
     def __init__(

@@ -151,6 +151,20 @@ def hashgrid_corners(x: torch.Tensor, grid) -> Tuple[torch.Tensor, torch.Tensor]
     return hashes.to(torch.int64) & 0xFFFFFFFF, weights
 
 
+def hashgrid_forward_rows(x: torch.Tensor, grid) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The production gather kernel (mri_hashgrid_forward's code path) with the table row of every corner recorded:
+    returns (encoding (n, L*F), rows (n, L, 2^D) int64 in the reference's corner order)."""
+    x2 = _lib.require_cuda_f32(x, "x").reshape(-1, grid.dim).contiguous()
+    n, c = x2.shape[0], 1 << grid.dim
+    tables = grid.tables()
+    grid._fwd_layout.refresh(tables, grid._resolutions, grid._rows)
+    out = torch.empty((n, grid.n_levels * grid.n_features_per_level), device=x.device, dtype=torch.float32)
+    rows = torch.full((n, grid.n_levels, c), -1, device=x.device, dtype=torch.int32)
+    _lib.call("mri_hashgrid_forward_rows", x2.data_ptr(), n, grid.dim, grid._fwd_layout.base, grid._fwd_layout.levels,
+              grid.n_levels, grid.n_features_per_level, out.data_ptr(), rows.data_ptr(), _lib.stream())
+    return out, rows.to(torch.int64) & 0xFFFFFFFF
+
+
 # -------------------------------------------------------------------------------- dense
 class DenseFn(torch.autograd.Function):
     """y = act(x W^T + b) - SirenLayer.forward (models.py:153-156) / decoder Linear+act."""

@@ -58,7 +58,8 @@ res = {"world": world, "steps": steps, "global_batch": n_global, "max_rel_param_
        "max_abs_replica_diff": replica_diff, "allreduces": dp_opt.allreduce_count, "overlap": bool(overlap), "sharded_p2p_adam": bool(dp_opt.sharded), "multimem": bool(getattr(dp_opt, "_grad_mc", 0)), "sweep_slabs_tile_exactly": ok_sweep}
 if rank == 0:
     print(json.dumps(res))
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"dp_parity_w{world}.json"), "w"))
+    out_dir = os.environ.get("MRI_DP_PARITY_OUT", os.path.join(ROOT, "gpurun_out"))
+    os.makedirs(out_dir, exist_ok=True)
+    json.dump(res, open(os.path.join(out_dir, f"dp_parity_w{world}.json"), "w"))
     assert worst < 1e-4 and replica_diff == 0.0 and ok_sweep and dp_opt.allreduce_count == steps, res
 dist.destroy_process_group()

@@ -27,6 +27,36 @@ def test_corner_hashes_bit_exact_and_weights(case):
 
 
 @pytest.mark.parametrize("case", HASH_CASES)
+def test_production_gather_addresses_exactly_the_reference_rows(case):
+    """The rows the SHIPPED gather kernel reads (hashgrid_fwd_kernel / encode_half_level with its row sink switched on,
+    not the corner probe) equal the reference's hashes bit for bit, and the instrumented launch returns the same
+    encoding as the plain one."""
+    fx = load_golden(f"hashgrid_{case}.npz")
+    enc = build_encoder(fx, DEV)
+    x = torch.from_numpy(fx["x"]).to(DEV)
+    out, rows = enc.gathered_rows(x)
+    assert np.array_equal(rows.cpu().numpy().astype(np.uint32), fx["hashes"])
+    with torch.no_grad():
+        assert torch.equal(out, enc(x))
+
+
+@pytest.mark.parametrize("case", HASH_CASES)
+def test_production_scatter_touches_exactly_the_reference_rows(case):
+    """Support of the table gradient written by the shipped scatter kernel == the set of reference rows with a
+    non-zero corner weight (one-hot probing of the production reduction path: a wrong index lands on another row)."""
+    fx = load_golden(f"hashgrid_{case}.npz")
+    enc = build_encoder(fx, DEV)
+    x = torch.from_numpy(fx["x"]).to(DEV)
+    out = enc(x)
+    out.backward(torch.ones_like(out))
+    hashes, weights = fx["hashes"].astype(np.int64), fx["weights"]
+    for li, lv in enumerate(enc.levels):
+        got = torch.nonzero(lv.embedding.weight.grad.abs().sum(1)).flatten().cpu().numpy()
+        want = np.unique(hashes[:, li][weights[:, li] != 0])
+        assert np.array_equal(got, want), f"level {li}"
+
+
+@pytest.mark.parametrize("case", HASH_CASES)
 def test_forward_backward_match_reference_vectors(case):
     fx = load_golden(f"hashgrid_{case}.npz")
     enc = build_encoder(fx, DEV)
@@ -111,6 +141,11 @@ def test_full_geometry_against_oracle_on_seeded_inputs(dim, kw):
     for li, lv in enumerate(levels):
         ho, _ = hashgrid.corners(x, lv)
         assert torch.equal(h[:, li].cpu(), ho), f"level {li} hashes differ"
+    out_rows, rows = enc.gathered_rows(x.to(DEV))  # the production gather path itself
+    assert torch.equal(out_rows, out.detach())
+    for li, lv in enumerate(levels):
+        ho, _ = hashgrid.corners(x, lv)
+        assert torch.equal(rows[:, li].cpu(), ho), f"level {li}: rows gathered by the production kernel differ"
     go = torch.randn(ref.shape, generator=gen)
     out.backward(go.to(DEV))
     gref = hashgrid.table_gradients(x, go, levels, 2)

@@ -367,6 +367,42 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(geo):
                 assert rel_err(pf.grad, ref) < 1e-3, (n, name)
 
 
+@pytest.mark.parametrize("geo", FUSED_GEOMETRIES)
+def test_fused_kernels_address_exactly_the_reference_rows(geo):
+    """Index exactness of the two kernels the bench times: (forward) the encoding written by hashdecoder_mma_fwd_kernel is
+    bit-identical to the stand-alone gather, whose addressed rows are asserted against the oracle's hashes; (backward)
+    the support of the table gradient left by hashdecoder_mma_bwd_kernel is exactly the oracle's set of hashed rows
+    with a non-zero corner weight."""
+    from mri_interpolation_b200 import models
+    from oracle import networks
+    dim = geo["dim_in"]
+    kw = dict(n_levels=16, n_features_per_level=2, dim_hidden=64, dim_out=1, n_layers=2, **geo)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
+    levels = networks.hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
+    net = net.to(DEV)
+    n = 777
+    x, y = torch.rand(n, dim, generator=gen), torch.rand(n, 1, generator=gen)
+    x[:4] = 0.0
+    x[4:8] = 1.0
+    pred = net(x.to(DEV))
+    assert type(pred.grad_fn).__name__.startswith("HashDecoderFn")
+    enc_rows, rows = net.encoder.gathered_rows(x.to(DEV))
+    enc_fused = pred.grad_fn.saved_tensors[1]  # the (n, 32) encoding the fused forward kernel wrote for its backward
+    assert torch.equal(enc_fused, enc_rows)
+    F.mse_loss(y.to(DEV), pred).backward()
+    for li, lv in enumerate(levels):
+        h, w = networks.hashgrid.corners(x, lv)
+        assert torch.equal(rows[:, li].cpu(), h), li
+        want = torch.unique(h[w != 0])
+        got = torch.nonzero(net.encoder.levels[li].embedding.weight.grad.abs().sum(1)).flatten().cpu()
+        assert torch.equal(got, want), f"level {li}: fused scatter touched other rows"
+
+
 @pytest.mark.parametrize("geo", [FUSED_GEOMETRIES[1], FUSED_GEOMETRIES[2]])
 @pytest.mark.parametrize("order", ["line", "line_descending", "dense_duplicates"])
 def test_fused_backward_merges_axis0_runs_of_locality_ordered_batches(geo, order):
