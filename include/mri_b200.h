@@ -263,6 +263,22 @@ int mri_hashmlp_sweep(const float* axes, const int32_t* host_shape, int dim, int
                       int n_levels, int n_features, const float* decoder, const int32_t* host_dims,
                       int n_dense, int act, int last_act, float* out, void* stream);
 
+/* ---- image-quality metrics and the linear-in-time baseline ------------------------ */
+
+/* *sum_out += sum_i (a[i] - b[i])^2 in double (device pointer, caller zero-fills): skimage mean_squared_error /
+ * peak_signal_noise_ratio of legacy_code/hash_experimentation.py:445-453 are sum/n and 10 log10(range^2 n / sum). */
+int mri_sq_err_sum(const float* a, const float* b, int64_t n, double* sum_out, void* stream);
+
+/* *sum_out += sum of the per-pixel SSIM index (skimage structural_similarity defaults: win x win uniform window,
+ * K1 = 0.01, K2 = 0.03, sample covariance) over the interior (borders of (win-1)/2 cropped) of every (axis 0, axis 1)
+ * plane of a, b shaped (nx, ny, planes) C-order; mean SSIM = sum / ((nx-win+1)(ny-win+1) planes). */
+int mri_ssim_sum(const float* a, const float* b, int nx, int ny, int64_t planes, int win, double data_range,
+                 double* sum_out, void* stream);
+
+/* interp.py:35-52 baseline: data, out (outer, t) C-order; out[o, f] = linear interpolation of the kept frames
+ * data[o, ::2] at continuous index min(f / 2, ceil(t / 2) - 1). */
+int mri_linear_time_interp(const float* data, int64_t outer, int t, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,9 @@ SIGNATURES = {
     "mri_siren_first_backward": [_P, _P, _I64, _I64, _I, _I, _P, _P, _P],
     "mri_siren_last_forward": [_P, _P, _P, _P, _I64, _I, _I, _P, _P],
     "mri_siren_last_backward": [_P, _P, _P, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _P, _P],
+    "mri_sq_err_sum": [_P, _P, _I64, _P, _P],
+    "mri_ssim_sum": [_P, _P, _I, _I, _I64, _I, _D, _P, _P],
+    "mri_linear_time_interp": [_P, _I64, _I, _P, _P],
 }
 _SPECIAL = {
     "mri_version": ([], _I),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmri_b200.so")
 SOURCES = ["core.cu", "hashgrid.cu", "dense.cu", "optim.cu", "sweep.cu", "siren_tc.cu", "decoder.cu", "siren_edge.cu", "hashdecoder_fwd.cu",
-           "hashdecoder_bwd.cu"]
+           "hashdecoder_bwd.cu", "metrics.cu"]
 HEADERS = ["common.cuh", "hash_device.cuh", "mma_device.cuh", "grid_device.cuh", "../../include/mri_b200.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -50,7 +50,7 @@ struct LevelDev {
   uint32_t rows;
   uint32_t pow2_mask;  // rows-1 if rows is a power of two, else 0xFFFFFFFF marker handled by is_pow2
   uint32_t is_pow2;
-  uint32_t pad;
+  uint32_t magic;      // floor(2^32 / rows): h % rows without a division (wrap_rows<false>)
   uint64_t offset;  // floats
 };
 struct LevelTable {
@@ -106,10 +106,17 @@ __device__ __forceinline__ float corner_weight(const Cell<D>& c, int n) {
 }
 // encoding.py:78 - true modulo; power-of-two tables take the mask shortcut.  POW2 is a template
 // parameter so the (block-uniform) choice is one branch per thread, not a predicate per corner.
+// Non-power-of-two tables: q = mulhi(h, floor(2^32 / rows)) is the true quotient or one less (the estimate falls short
+// of h / rows by less than 1), so one conditional subtraction gives exactly h % rows - 4 instructions instead of the
+// ~25 of a 32-bit division.
+__device__ __forceinline__ uint32_t exact_mod(uint32_t h, uint32_t rows, uint32_t magic) {
+  const uint32_t r = h - __umulhi(h, magic) * rows;
+  return r >= rows ? r - rows : r;
+}
 template <bool POW2>
 __device__ __forceinline__ uint32_t wrap_rows(uint32_t h, const LevelDev& lv) {
   if constexpr (POW2) return h & lv.pow2_mask;
-  else return h % lv.rows;
+  else return exact_mod(h, lv.rows, lv.magic);
 }
 
 template <int D>
@@ -129,15 +136,27 @@ __device__ __forceinline__ void load_coord(const float* __restrict__ x, int64_t 
 // erf-GELU (nn.GELU default, approximate='none') and its derivative.  Phi(x) = 0.5 (1 + erf(x/sqrt2)) is
 // evaluated with the Abramowitz-Stegun 7.1.26 rational form (|abs err| <= 1.5e-7, far inside the 1e-3 parity
 // bound): one MUFU.RCP + one MUFU.EX2 + 5 FMA, and exp(-x^2/2) is shared with the Gaussian pdf of the derivative.
+// The SFU approximations are issued directly (rcp.approx / ex2.approx, ~1-2 ulp): __frcp_rn adds a Newton step and
+// a range-check branch with a slow-path call per element, __expf a denormal fix-up - in the fused backward kernel this
+// function is evaluated 32 times per lane and tile and was a quarter of all issued instructions (ncu source page).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_cdf_pdf(float x, float& cdf, float& pdf) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  const float e = __expf(-0.5f * x * x);  // = exp(-z^2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float half_erfc = 0.5f * poly * t * e;  // 0.5 * erfc(z)
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  const float e = ex2_approx(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2) = exp(-z^2), z = |x| / sqrt(2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);  // the 0.5 of 0.5 erfc(z) folded into the coefficients
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float half_erfc = poly * t * e;  // 0.5 * erfc(z)
   cdf = x >= 0.0f ? 1.0f - half_erfc : half_erfc;
   pdf = 0.39894228040143267794f * e;
 }

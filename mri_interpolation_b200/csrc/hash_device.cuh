@@ -111,37 +111,17 @@ __device__ __forceinline__ void scatter_half_level(const Cell<D>& cell, int b0, 
   }
 }
 
-// Both rows of an m-tile at one level (F = 2), for the fused forward: power-of-two tables take the unrolled mask path
-// with all 2 * 2^(D-1) gathers of the two rows in flight together; the few other (coarse) levels run a compact loop with
-// the true modulo, so the rarely executed variant does not double the kernel's instruction footprint.
+// Both rows of an m-tile at one level (F = 2), for the fused forward: one branch per level, both rows inside it, so all
+// 2 * 2^(D-1) gathers of the two rows are in flight together.
 template <int D>
 __device__ __forceinline__ void encode_half_level_rows(const Cell<D>& ca, const Cell<D>& cb, int b0, const LevelDev& lv,
                                                        const float* __restrict__ tbl, Feat<2>& oa, Feat<2>& ob) {
-  constexpr int CH = 1 << (D - 1);
   if (lv.is_pow2) {
     oa = encode_half_level<D, 2, true>(ca, b0, lv, tbl);
     ob = encode_half_level<D, 2, true>(cb, b0, lv, tbl);
-    return;
-  }
-  const uint32_t ta = ca.lo[0] + static_cast<uint32_t>(b0), tb = cb.lo[0] + static_cast<uint32_t>(b0);
-  const float wa0 = b0 ? ca.wu[0] : ca.wl[0], wb0 = b0 ? cb.wu[0] : cb.wl[0];
-  oa.v[0] = oa.v[1] = ob.v[0] = ob.v[1] = 0.0f;
-#pragma unroll 1
-  for (int c = 0; c < CH; ++c) {
-    uint32_t ha = ta, hb = tb;
-    float wa = wa0, wb = wb0;
-#pragma unroll
-    for (int d = 1; d < D; ++d) {
-      const bool up = (c >> (d - 1)) & 1;
-      ha ^= up ? (ca.lo[d] + prime(d)) : ca.lo[d];
-      hb ^= up ? (cb.lo[d] + prime(d)) : cb.lo[d];
-      wa = __fmul_rn(wa, up ? ca.wu[d] : ca.wl[d]);
-      wb = __fmul_rn(wb, up ? cb.wu[d] : cb.wl[d]);
-    }
-    const Feat<2> ra = gather_row<2>(tbl + static_cast<size_t>(ha % lv.rows) * 2);
-    const Feat<2> rb = gather_row<2>(tbl + static_cast<size_t>(hb % lv.rows) * 2);
-    oa.v[0] = fmaf(ra.v[0], wa, oa.v[0]); oa.v[1] = fmaf(ra.v[1], wa, oa.v[1]);
-    ob.v[0] = fmaf(rb.v[0], wb, ob.v[0]); ob.v[1] = fmaf(rb.v[1], wb, ob.v[1]);
+  } else {  // a few coarse levels (res^D < T): exact modulo by multiplication (wrap_rows<false>), same straight-line shape
+    oa = encode_half_level<D, 2, false>(ca, b0, lv, tbl);
+    ob = encode_half_level<D, 2, false>(cb, b0, lv, tbl);
   }
 }
 
@@ -198,41 +178,37 @@ __device__ __forceinline__ MergedHalf merge_line_runs(uint32_t kk, float v0, flo
   return r;
 }
 
-// scatter of one half level whose value (v0, v1) already carries the axis-0 weight (F = 2).  Power-of-two tables (all
-// but a few coarse levels) take the unrolled mask path; the others go through a compact loop with the true modulo so
-// that the rarely executed variant does not double the instruction footprint of the fused kernels.
+// scatter of one half level whose value (v0, v1) already carries the axis-0 weight (F = 2).  The hashes of all corners
+// are formed first; power-of-two tables mask them (fused into the XOR by the compiler), the few non-power-of-two coarse
+// levels reduce them with the multiply-based exact modulo, and ONE copy of the weight / reduction code serves both.
 template <int D>
 __device__ __forceinline__ void scatter_half_level_weighted(const Cell<D>& cell, int b0, const LevelDev& lv, float* tbl, float v0, float v1) {
   constexpr int CH = 1 << (D - 1);
   const uint32_t t0 = cell.lo[0] + static_cast<uint32_t>(b0);
+  uint32_t row[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    uint32_t h = t0;
+#pragma unroll
+    for (int d = 1; d < D; ++d) h ^= ((c >> (d - 1)) & 1) ? (cell.lo[d] + prime(d)) : cell.lo[d];
+    row[c] = h;
+  }
   if (lv.is_pow2) {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      uint32_t h = t0;
-      float w = 1.0f;
-#pragma unroll
-      for (int d = 1; d < D; ++d) {
-        const bool up = (c >> (d - 1)) & 1;
-        h ^= up ? (cell.lo[d] + prime(d)) : cell.lo[d];
-        const float wd = up ? cell.wu[d] : cell.wl[d];
-        w = d == 1 ? wd : __fmul_rn(w, wd);
-      }
-      red_add_v2(tbl + static_cast<size_t>(h & lv.pow2_mask) * 2, v0 * w, v1 * w);
-    }
+    for (int c = 0; c < CH; ++c) row[c] &= lv.pow2_mask;
   } else {
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c) {
-      uint32_t h = t0;
-      float w = 1.0f;
 #pragma unroll
-      for (int d = 1; d < D; ++d) {
-        const bool up = (c >> (d - 1)) & 1;
-        h ^= up ? (cell.lo[d] + prime(d)) : cell.lo[d];
-        const float wd = up ? cell.wu[d] : cell.wl[d];
-        w = d == 1 ? wd : __fmul_rn(w, wd);
-      }
-      red_add_v2(tbl + static_cast<size_t>(h % lv.rows) * 2, v0 * w, v1 * w);
+    for (int c = 0; c < CH; ++c) row[c] = exact_mod(row[c], lv.rows, lv.magic);
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    float w = 1.0f;
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const float wd = ((c >> (d - 1)) & 1) ? cell.wu[d] : cell.wl[d];
+      w = d == 1 ? wd : __fmul_rn(w, wd);
     }
+    red_add_v2(tbl + static_cast<size_t>(row[c]) * 2, v0 * w, v1 * w);
   }
 }
 

@@ -358,16 +358,15 @@ extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, cons
   int st = make_level_table(host_levels, n_levels, dim, &T);
   if (st != MRI_OK) return st;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // MRI_BWD_MERGE_LEVELS = 0 | 8 | 12: number of coarse levels whose axis-0 duplicates are merged before the reduction
-  // (default 8; 0 switches the merging off for A/B runs); MRI_BWD_CONTIGUOUS=0 restores the grid-stride tile walk
+  // MRI_BWD_MERGE_LEVELS = 0 | 4 | 8: number of coarse levels whose axis-0 duplicates are merged before the reduction
+  // (default 8; 0 switches the merging off for A/B runs)
   static const int merge_nt2 = [] {
     const char* e = getenv("MRI_BWD_MERGE_LEVELS");
     const int v = e ? atoi(e) : 8;
-    return v <= 0 ? 0 : v >= 12 ? 3 : 2;
+    return v <= 0 ? 0 : v <= 4 ? 1 : 2;
   }();
-  static const bool contiguous = [] { const char* e = getenv("MRI_BWD_CONTIGUOUS"); return !e || atoi(e) != 0; }();
 #define CALL(DV, ACTV, MV, CV) launch_fused_bwd<DV, 32, 64, ACTV, MV, CV>(enc, n, w1, b1, w2, pre2, grad_y, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2, grad_b2, s)
-#define CALL_M(DV, ACTV) (!contiguous ? CALL(DV, ACTV, 2, false) : merge_nt2 == 0 ? CALL(DV, ACTV, 0, true) : merge_nt2 == 2 ? CALL(DV, ACTV, 2, true) : CALL(DV, ACTV, 3, true))
+#define CALL_M(DV, ACTV) (merge_nt2 == 0 ? CALL(DV, ACTV, 0, true) : merge_nt2 == 1 ? CALL(DV, ACTV, 1, true) : CALL(DV, ACTV, 2, true))
   if (dim == 4 && act1 == MRI_ACT_GELU) return CALL_M(4, MRI_ACT_GELU);
   if (dim == 4 && act1 == MRI_ACT_RELU) return CALL_M(4, MRI_ACT_RELU);
   if (dim == 3 && act1 == MRI_ACT_GELU) return CALL_M(3, MRI_ACT_GELU);

@@ -98,7 +98,7 @@ struct SweepCoordsAxis0 {
 };
 
 template <int D, int K0, int H, int ACT1, class Coords>
-__global__ void __launch_bounds__(DEC_THREADS, 3) hashdecoder_mma_fwd_kernel(const Coords src, int64_t n,
+__global__ void __launch_bounds__(DEC_THREADS, 5) hashdecoder_mma_fwd_kernel(const Coords src, int64_t n,
                                                                              const float* __restrict__ tables,
                                                                              const __grid_constant__ LevelTable T,
                                                                              const float* __restrict__ w1, const float* __restrict__ b1,

@@ -147,6 +147,7 @@ int make_level_table(const mri_level_t* host_levels, int n_levels, int dim, Leve
     d.rows = h.rows;
     d.is_pow2 = (h.rows & (h.rows - 1)) == 0 ? 1u : 0u;
     d.pow2_mask = h.rows - 1;
+    d.magic = h.rows > 1 ? static_cast<uint32_t>((uint64_t{1} << 32) / h.rows) : 0xffffffffu;
     d.offset = h.offset;
   }
   return MRI_OK;

@@ -14,12 +14,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// (x, y) -> packed bf16 pairs hi = (bf16(x), bf16(y)) and lo = (bf16(x - hi.x), bf16(y - hi.y)), x in the low half.
+// Two packed conversions (F2FP.BF16.PACK_AB) with the high parts read back by a shift / mask: 6 instructions, where
+// two scalar conversions + a permute took 8 (the split runs on every A fragment of every product).
 __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
-  const __nv_bfloat162 h = __halves2bfloat162(hx, hy);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x - __bfloat162float(hx), y - __bfloat162float(hy));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - yh), "f"(x - xh));
 }
 
 constexpr int MMA_PAD = 8;  // bf16 elements of row padding: conflict-free 32-bit fragment loads

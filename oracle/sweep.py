@@ -59,6 +59,18 @@ def linear_time_interpolation(frames: np.ndarray, n_out: int) -> np.ndarray:
     return frames[..., lo] * (1 - a) + frames[..., hi] * a
 
 
+def linear_time_baseline(data: np.ndarray) -> np.ndarray:
+    """interp.py:35-50 as the reference runs it: keep frames ::2 and evaluate the ITK linear interpolator at the
+    continuous index t/2 along the last axis for every output frame t (clamped at the last kept frame)."""
+    values = data[..., ::2]
+    t_in = values.shape[-1]
+    pos = np.minimum(np.arange(data.shape[-1]) / 2.0, t_in - 1)
+    lo = np.floor(pos).astype(np.int64)
+    hi = np.minimum(lo + 1, t_in - 1)
+    a = (pos - lo).astype(data.dtype)
+    return values[..., lo] * (1 - a) + values[..., hi] * a
+
+
 def psnr(truth: np.ndarray, test: np.ndarray, data_range: float = 1.0) -> float:
     """10 log10(data_range^2 / MSE), float64 accumulation (skimage's definition)."""
     err = np.mean((truth.astype(np.float64) - test.astype(np.float64)) ** 2)

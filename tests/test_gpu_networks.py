@@ -384,6 +384,7 @@ def test_fused_kernels_address_exactly_the_reference_rows(geo):
         for lv in net.encoder.levels:
             lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
     levels = networks.hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
+    aniso = not isinstance(geo["base_resolution"], int)
     net = net.to(DEV)
     n = 777
     x, y = torch.rand(n, dim, generator=gen), torch.rand(n, 1, generator=gen)
@@ -396,7 +397,7 @@ def test_fused_kernels_address_exactly_the_reference_rows(geo):
     assert torch.equal(enc_fused, enc_rows)
     F.mse_loss(y.to(DEV), pred).backward()
     for li, lv in enumerate(levels):
-        h, w = networks.hashgrid.corners(x, lv)
+        h, w = networks.hashgrid.corners(x, lv, aniso)
         assert torch.equal(rows[:, li].cpu(), h), li
         want = torch.unique(h[w != 0])
         got = torch.nonzero(net.encoder.levels[li].embedding.weight.grad.abs().sum(1)).flatten().cpu()
