@@ -45,10 +45,14 @@ SAMPLE = os.path.join(ROOT, "data", "sample_ankle_dyn_mri.nii.gz")
 SWEEP_SHAPE = (352, 352, 6, 29)  # 2x time up-sampling of the sample volume (config 3)
 PRIMING_STEPS = 15  # allocator priming before the W warm-up steps (reported in config)
 HASH_BYTES_PER_COORD = 4 * 4 + 16 * 16 * 2 * 4 + 16 * 2 * 4  # 4D + L*2^D*F*4 + L*F*4 = 2192
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at 2^19 locality-ordered coords, from the ncu --set full
-# capture of THIS kernel version committed as profiles/r02_ncu_full_fused_hashdecoder.csv (same command, --steps 3)
-NCU_DRAM_BYTES = {"hashdecoder_bwd": 142.2e6 + 184.7e6, "hashdecoder_fwd": 86.7e6 + 60.0e6}
+# Fallback for roofline.traffic when the live ncu probe (traffic_probe below) cannot run: dram__bytes_read.sum +
+# dram__bytes_write.sum and L2 reduction / L1 load sectors per launch at 2^19 locality-ordered coords, from the
+# ncu --set full capture committed as profiles/r02_ncu_full_fused_hashdecoder.csv
+NCU_DRAM_BYTES = {"hashdecoder_bwd": 142.2e6 + 149.4e6, "hashdecoder_fwd": 87.5e6 + 56.7e6}
+NCU_RED_SECTORS = {"hashdecoder_bwd": 74.97e6}
 NCU_SOURCE = "profiles/r02_ncu_full_fused_hashdecoder.csv"
+PROBE_METRICS = ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+                 "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum")
 SUSTAIN_SECONDS = 0.6
 
 
@@ -80,6 +84,9 @@ def parse():
     ap.add_argument("--no-infer", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short legs of configs 1/4/5 after the headline")
+    ap.add_argument("--no-traffic-probe", action="store_true",
+                    help="skip the nested ncu run that measures roofline.traffic (DRAM bytes, L2 reduction sectors) on this box")
+    ap.add_argument("--probe-steps", type=int, default=0, help=argparse.SUPPRESS)  # child of the traffic probe: N plain steps, no output
     args = ap.parse_args()
     if args.batch_log2 is None:
         args.batch_log2 = WORKLOADS[args.workload][1]
@@ -364,6 +371,80 @@ def draw_index_ring(name, sampler, info, n, ring, dev, rank, world):
     return index, ms, how
 
 
+def traffic_probe(args, batch_log2):
+    """roofline.traffic measured on THIS box in THIS run: a nested `ncu --metrics ...` run of this script (--probe-steps:
+    the same workload and batch size, a handful of plain training steps) captures one steady-state launch of each fused
+    kernel and returns {kernel: {metric: value}}.  Byte / sector counters only - no timing is taken under the profiler.
+    Returns (None, reason) when ncu is absent or the counters are not accessible."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.isfile(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", ",".join(PROBE_METRICS), "--clock-control", "none", "--print-units", "base", "-k",
+           "regex:hashdecoder_mma_(fwd|bwd)_kernel", "-s", "8", "-c", "2", "--csv", sys.executable, os.path.abspath(__file__),
+           "--probe-steps", "8", "--workload", args.workload, "--batch-log2", str(batch_log2)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        run = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    except Exception as e:  # noqa: BLE001
+        return None, f"ncu probe failed: {type(e).__name__}"
+    rows = list(csv.reader(io.StringIO(run.stdout[run.stdout.find('"ID"'):]))) if '"ID"' in run.stdout else []
+    if run.returncode != 0 or len(rows) < 2:
+        return None, f"ncu probe rc={run.returncode}: {(run.stdout + run.stderr).strip()[-200:]}"
+    col = {h: i for i, h in enumerate(rows[0])}
+    out = {}
+    for r in rows[1:]:
+        if len(r) <= col["Metric Value"]:
+            continue
+        kname = "hashdecoder_bwd" if "hashdecoder_mma_bwd" in r[col["Kernel Name"]] else "hashdecoder_fwd"
+        try:
+            out.setdefault(kname, {})[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", ""))
+        except ValueError:
+            pass
+    return (out, "ncu, nested run of this command on this box") if out else (None, "ncu probe returned no metrics")
+
+
+def probe_main(args):
+    """Child of traffic_probe: the headline workload's plain training steps, nothing timed, nothing printed."""
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    model, sampler, info = build_workload(args.workload, dev)
+    opt = model.configure_optimizers()
+    n = 1 << args.batch_log2
+    index, _, _ = draw_index_ring(args.workload, sampler, info, n, 4, dev, 0, 1)
+    for i in range(args.probe_steps):
+        x, y = sampler.batch(index[i % 4])
+        model.training_step((x, y), i).backward()
+        opt.step()
+        opt.zero_grad()
+    torch.cuda.synchronize()
+
+
+def red_rate_peak(dev):
+    """Peak L2 sector-reduction rate of this GPU (csrc/probe.cu), G sector-ops/s: {spread: 32 sectors per warp
+    instruction, paired: adjacent lanes share a sector like the pair-lane scatter}."""
+    import ctypes
+    from mri_interpolation_b200 import _lib
+    table = torch.zeros(16 << 20, device=dev)  # 64 MB: L2-resident like the 61 MB gradient arena
+    ops = ctypes.c_int64(0)
+    out = {}
+    for name, lanes in (("spread", 1), ("paired", 2)):
+        best = None
+        for rep in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.call("mri_probe_red_rate", table.data_ptr(), table.numel(), 64, lanes, ctypes.byref(ops), _lib.stream())
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            best = ms if best is None or (rep > 0 and ms < best) else best
+        out[name] = ops.value / (best * 1e-3) / 1e9
+    del table
+    return out
+
+
 def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world, *, e2e=True, infer=True, kernels=True):
     """One workload: timed training steps (+ sustained window with clocks), e2e, inference sweep, isolated kernels."""
     import torch.distributed as dist
@@ -605,19 +686,43 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
                                            "frac": (fused_bytes + 4 * n) / fused_fwd_ms / 1e6 / hbm_peak}
                 top = "hashdecoder_bwd" if fused_ms >= fused_fwd_ms else "hashdecoder_fwd"
                 hash_bytes = fused_bytes if top == "hashdecoder_bwd" else fused_bytes + 4 * n
-                # ncu DRAM bytes were captured at 2^19 ankle-volume coords; other sizes / volumes have no capture
-                traffic = NCU_DRAM_BYTES[top] if (name == "ankle_hash" and batch_log2 == 19) else None
+                # DRAM bytes and L2 reduction sectors per launch: measured now by a nested ncu run (headline leg only),
+                # else the committed capture (2^19 ankle-volume coords; other sizes / volumes have none)
+                probe, traffic_src = (None, "probe skipped")
+                if name == args.workload and not args.no_traffic_probe and world == 1:
+                    probe, traffic_src = traffic_probe(args, batch_log2)
+                red_sectors = None
+                if probe and top in probe and "dram__bytes_read.sum" in probe[top]:
+                    traffic = probe[top]["dram__bytes_read.sum"] + probe[top]["dram__bytes_write.sum"]
+                    red_sectors = probe.get("hashdecoder_bwd", {}).get("lts__t_sectors_srcunit_tex_op_red.sum")
+                elif name == "ankle_hash" and batch_log2 == 19:
+                    traffic, traffic_src = NCU_DRAM_BYTES[top], NCU_SOURCE + f" (live probe: {traffic_src})"
+                    red_sectors = NCU_RED_SECTORS["hashdecoder_bwd"]
+                else:
+                    traffic_src = None
             step_bytes = (2 * HASH_BYTES_PER_COORD + 8) * n + adam_bytes  # fused fwd + fused bwd + Adam, algorithmic
             kern["whole_step"] = {"ms": ms_step, "algorithmic_GB": step_bytes / 1e9, "GBps_algorithmic": step_bytes / ms_step / 1e6,
                                   "frac": step_bytes / ms_step / 1e6 / hbm_peak}
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": NCU_SOURCE if traffic else None,
+                    "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": traffic_src if fused_ms is not None else None,
                     "peak_source": peak_src + " hbm_gbs", "algorithmic_bytes_per_launch": hash_bytes,
                     "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x coords per launch (+4 B/coord dy "
                             "for the fused decoder-backward+scatter kernel, which also does 8.4 kMAC/coord of decoder math); "
                             "traffic = ncu dram read+write per launch: the 61 MB of tables stay in the 126 MB L2, so DRAM moves "
                             "less than the algorithmic bytes - the kernels are bound by the L2 sector / L2 atomic rates "
                             "(DESIGN.md 3), not HBM"}
+            if fused_ms is not None and red_sectors:
+                # the resource that actually binds the backward: 32-byte sector reductions retired by the L2 atomic units
+                peak = red_rate_peak(dev)
+                ach = red_sectors / (fused_ms * 1e-3) / 1e9
+                roof["binding"] = {"resource": "L2 atomic units: 32-byte sector reductions (red.global.add.v2.f32)",
+                                   "kernel": "hashdecoder_bwd", "sector_ops_per_launch": red_sectors, "achieved": ach,
+                                   "peak": peak["paired"], "peak_spread": peak["spread"], "unit": "G sector-ops/s",
+                                   "frac": ach / peak["paired"],
+                                   "peak_source": "measured in this run by mri_probe_red_rate (csrc/probe.cu): every warp instruction "
+                                                  "reduces into 16 (paired, the scatter's own pattern) / 32 (spread) distinct sectors "
+                                                  "of an L2-resident 64 MB table, 4 CTAs of 128 threads per SM",
+                                   "sector_source": traffic_src}
         else:
             from mri_interpolation_b200 import tc
             from mri_interpolation_b200._lib import ACT_SINE
@@ -673,6 +778,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+
+    if args.probe_steps > 0:
+        probe_main(args)
         return
 
     from mri_interpolation_b200 import distributed

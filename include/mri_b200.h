@@ -279,6 +279,15 @@ int mri_ssim_sum(const float* a, const float* b, int nx, int ny, int64_t planes,
  * data[o, ::2] at continuous index min(f / 2, ceil(t / 2) - 1). */
 int mri_linear_time_interp(const float* data, int64_t outer, int t, float* out, void* stream);
 
+/* ---- measurement probe (bench.py only) ------------------------------------------------------------ */
+
+/* Peak rate of 32-byte sector reductions at the L2: red.global.add.v2.f32 from every lane into pseudo-random sectors of
+ * `table` (table_floats floats, L2-resident sizes), `lanes_per_sector` = 1 (32 sector operations per warp instruction)
+ * or 2 (adjacent lanes share a sector, as the pair-lane scatter does).  *sector_ops (host) = operations one launch
+ * issues; the caller times the launch.  The roofline the fused backward kernel is reported against besides HBM. */
+int mri_probe_red_rate(float* table, int64_t table_floats, int iters, int lanes_per_sector, int64_t* sector_ops,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,7 @@ SIGNATURES = {
     "mri_sq_err_sum": [_P, _P, _I64, _P, _P],
     "mri_ssim_sum": [_P, _P, _I, _I, _I64, _I, _D, _P, _P],
     "mri_linear_time_interp": [_P, _I64, _I, _P, _P],
+    "mri_probe_red_rate": [_P, _I64, _I, _I, ctypes.POINTER(ctypes.c_int64), _P],
 }
 _SPECIAL = {
     "mri_version": ([], _I),

@@ -1,340 +1,9 @@
 // Backward of the whole HashMLP in ONE kernel: decoder backward on the tensor cores (decoder.cu's
 // decoder2_mma_bwd_kernel arithmetic) with the hash-table scatter fused in (autograd of models.py:741-744 on top of
-// encoding.py:127-128), for the headline geometry F = 2, L = 16 (K0 = 32), H = 64, D = 3 / 4.
-#include <cuda_bf16.h>
-#include <stdlib.h>
-
-#include "common.cuh"
-#include "hash_device.cuh"
-#include "mma_device.cuh"
-
-namespace mri {
-namespace {
-
-constexpr int BWD_WARPS = 6;               // 192 threads, 2 blocks per SM (168 registers): 12 warps per SM
-constexpr int BWD_THREADS = 32 * BWD_WARPS;
-
-template <int K0, int H>
-constexpr size_t fused_bwd_smem_bytes() {
-  return 2 * (H * (K0 + MMA_PAD) + K0 * (H + MMA_PAD)) * sizeof(__nv_bfloat16)  // W1 and W1^T planes
-         + 2 * H * sizeof(float)                                               // b1, w2
-         + BWD_WARPS * (2 * 16 * ((H + MMA_PAD) + (K0 + MMA_PAD)) * sizeof(__nv_bfloat16)  // per-warp dPre1 / enc planes of one m-tile
-                        + H * K0 * sizeof(float));                                          // per-warp dW1 accumulator
-}
-
-// Decoder backward on the tensor cores with the table scatter fused in.  Per warp and per 16-coordinate m-tile:
-//   (1) recompute pre1 = enc W1^T + b1 (mma.sync, as in the forward), form dPre1 = dPre2 w2 act1'(pre1) on the fragments
-//   (2) dEnc = dPre1 W1: the accumulator fragments ARE the A fragments of the next mma (no data movement); all four
-//       8-column blocks are issued back to back (four independent accumulator chains)
-//   (3) dW1 += dPre1^T enc: both operands go through warp-private shared memory and come back transposed with
-//       ldmatrix.trans; the 64 x 32 fp32 accumulator lives in warp-private shared memory in fragment order and passes
-//       through registers only here - keeping it in registers for the whole loop (round 1) cost 64 of 253 registers and
-//       held the kernel at 8 warps per SM, where ncu showed it latency-bound (issue slots 26-32 % busy)
-//   (4) scatter: the dEnc fragments (rows g / g+8, level 4*nt2 + t for F = 2) never go to memory - lane pairs (t even /
-//       odd) exchange their two levels with one shuffle and act as the lower / upper axis-0 halves of the pair-lane
-//       scatter (hash_device.cuh); on the coarse levels duplicates along an axis-0 line are merged first.
-// db1 / dw2 / db2 are per-thread column partials reduced once at the end.
-template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
-__global__ void __launch_bounds__(BWD_THREADS, 2) hashdecoder_mma_bwd_kernel(const float* __restrict__ enc, int64_t n,
-                                                                           const float* __restrict__ w1, const float* __restrict__ b1,
-                                                                           const float* __restrict__ w2, const float* __restrict__ pre2,
-                                                                           const float* __restrict__ gy, int act2,
-                                                                           const float* __restrict__ x, const __grid_constant__ LevelTable T,
-                                                                           float* __restrict__ grad_tables, float* __restrict__ gw1,
-                                                                           float* __restrict__ gb1, float* __restrict__ gw2,
-                                                                           float* __restrict__ gb2) {
-  static_assert(K0 == 32 && H % 16 == 0, "F = 2, L = 16");
-  constexpr int WS = K0 + MMA_PAD;   // row stride of W1 / enc planes (bf16 elements)
-  constexpr int TS = H + MMA_PAD;    // row stride of W1^T / dPre1 planes
-  constexpr int STAGE = 2 * 16 * (TS + WS);  // bf16 elements of one warp's staging area
-  extern __shared__ __align__(16) uint8_t msm[];
-  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(msm);   // [H][WS]
-  __nv_bfloat16* w_lo = w_hi + H * WS;
-  __nv_bfloat16* wt_hi = w_lo + H * WS;                           // [K0][TS]  (W1 transposed)
-  __nv_bfloat16* wt_lo = wt_hi + K0 * TS;
-  float* b1s = reinterpret_cast<float*>(wt_lo + K0 * TS);
-  float* w2s = b1s + H;
-  float* wacc_all = w2s + H;                                      // [BWD_WARPS][H/16][K0/8][32 lanes][4]
-  __nv_bfloat16* stage_all = reinterpret_cast<__nv_bfloat16*>(wacc_all + BWD_WARPS * H * K0);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  float4* wacc_s = reinterpret_cast<float4*>(wacc_all + warp * H * K0) + lane;   // + 32 * (jt * K0/8 + nt2)
-  __nv_bfloat16* dp_hi = stage_all + warp * STAGE;                 // [16][TS]
-  __nv_bfloat16* dp_lo = dp_hi + 16 * TS;
-  __nv_bfloat16* e_hi = dp_lo + 16 * TS;                           // [16][WS]
-  __nv_bfloat16* e_lo = e_hi + 16 * WS;
-
-  stage_planes<H, K0>(w1, w_hi, w_lo, false);
-  stage_planes<H, K0>(w1, wt_hi, wt_lo, true);
-  for (int e = threadIdx.x; e < H; e += blockDim.x) {
-    b1s[e] = __ldg(b1 + e);
-    w2s[e] = __ldg(w2 + e);
-  }
-  for (int e = threadIdx.x; e < BWD_WARPS * H * K0; e += blockDim.x) wacc_all[e] = 0.0f;
-  // the lanes of one instruction work on two different levels: a lane-indexed read of the __grid_constant__ table is a
-  // replayed LDC on the long scoreboard (17 % of the stall samples in ncu) - shared memory serves it in one pass
-  __shared__ LevelDev lvs[K0 / 2];
-  if (threadIdx.x < K0 / 2) lvs[threadIdx.x] = T.lv[threadIdx.x];
-  __syncthreads();
-
-  float pb1[H / 8][2], pw2[H / 8][2];
-#pragma unroll
-  for (int nt = 0; nt < H / 8; ++nt) { pb1[nt][0] = pb1[nt][1] = 0.0f; pw2[nt][0] = pw2[nt][1] = 0.0f; }
-  float pb2 = 0.0f;
-
-  // inputs of one 16-row m-tile as they come out of global memory; the next tile's are requested before the current
-  // tile is processed
-  struct TileIn {
-    float2 e[K0 / 16][2][2];  // [k-tile][8-column half][row g / g+8]
-    float gy[2], p2[2];
-    float xv[2][D];
-  };
-  auto fetch = [&](int64_t row0, TileIn& ti) {
-    const int64_t r[2] = {row0 + g, row0 + g + 8};
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const bool live = r[rr] < n;
-      load_coord<D>(x, live ? r[rr] : 0, ti.xv[rr]);
-      ti.gy[rr] = live ? __ldg(gy + r[rr]) : 0.0f;
-      ti.p2[rr] = live ? __ldg(pre2 + r[rr]) : 0.0f;
-#pragma unroll
-      for (int kt = 0; kt < K0 / 16; ++kt)
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-          ti.e[kt][half][rr] = live ? __ldg(reinterpret_cast<const float2*>(enc + r[rr] * K0 + 16 * kt + 8 * half + 2 * t))
-                                    : make_float2(0.0f, 0.0f);
-    }
-  };
-
-  // Every warp walks its OWN contiguous range of m-tiles.  With a locality-ordered batch a grid-stride walk would make
-  // all resident warps work on neighbouring samples at the same time, i.e. reduce into the same few rows of the coarse
-  // levels at once - and the L2 serialises reductions on one address (measured: 2.2x slower when 8192 rows are hot
-  // grid-wide).  Warps that are far apart in the batch are far apart in the volume.
-  const int64_t tiles = (n + 15) / 16;
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * BWD_WARPS;
-  const int64_t wid = static_cast<int64_t>(blockIdx.x) * BWD_WARPS + warp;
-  const int64_t tile_end = CONTIGUOUS ? ((wid + 1) * tiles) / n_warps : tiles;
-  const int64_t tile_stride = CONTIGUOUS ? 1 : n_warps;
-  int64_t tile = CONTIGUOUS ? (wid * tiles) / n_warps : wid;
-  TileIn nxt;
-  fetch(tile * 16, nxt);
-#pragma unroll 1
-  for (; tile < tile_end; tile += tile_stride) {
-    const int64_t row0 = tile * 16;
-    const int64_t r_lo = row0 + g, r_hi = row0 + g + 8;
-    const TileIn cur = nxt;
-    fetch((tile + tile_stride) * 16, nxt);
-    float xv_lo[D], xv_hi[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) { xv_lo[d] = cur.xv[0][d]; xv_hi[d] = cur.xv[1][d]; }
-    // rows g, g+1 of an 8-row group live and on one axis-0 line (identical coordinates on every other axis)
-    uint32_t line_mask[2] = {0u, 0u};
-    if constexpr (MERGE_NT2 > 0) {
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        bool same = g < 7 && (rr == 0 ? r_lo : r_hi) + 1 < n;
-#pragma unroll
-        for (int d = 1; d < D; ++d) {
-          const float mine = rr == 0 ? xv_lo[d] : xv_hi[d];
-          const float next = __shfl_down_sync(0xffffffffu, mine, 4);  // every lane takes part: no short-circuit around it
-          same = same && next == mine;
-        }
-        line_mask[rr] = __ballot_sync(0xffffffffu, same);
-      }
-    }
-    float acc[H / 8][4];
-    {
-      uint32_t a_hi[K0 / 16][4], a_lo[K0 / 16][4];
-#pragma unroll
-      for (int kt = 0; kt < K0 / 16; ++kt)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
-          split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
-        }
-#pragma unroll
-      for (int kt = 0; kt < K0 / 16; ++kt)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int col = 16 * kt + 8 * half + 2 * t;
-          *reinterpret_cast<uint32_t*>(e_hi + g * WS + col) = a_hi[kt][2 * half];
-          *reinterpret_cast<uint32_t*>(e_lo + g * WS + col) = a_lo[kt][2 * half];
-          *reinterpret_cast<uint32_t*>(e_hi + (g + 8) * WS + col) = a_hi[kt][2 * half + 1];
-          *reinterpret_cast<uint32_t*>(e_lo + (g + 8) * WS + col) = a_lo[kt][2 * half + 1];
-        }
-      hidden_mma<K0, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
-    }
-    float dp2_lo = 0.0f, dp2_hi = 0.0f;
-    if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
-    if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
-    if (t == 0) pb2 += dp2_lo + dp2_hi;
-    float dacc[K0 / 8][4];
-    {
-      uint32_t da_hi[H / 16][4], da_lo[H / 16][4];
-#pragma unroll
-      for (int nt = 0; nt < H / 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float dp2 = e < 2 ? dp2_lo : dp2_hi;
-          float a, gp;
-          act_and_grad<ACT1>(acc[nt][e], a, gp);
-          pw2[nt][e & 1] = fmaf(dp2, a, pw2[nt][e & 1]);
-          const float dpre = dp2 * w2s[8 * nt + 2 * t + (e & 1)] * gp;
-          pb1[nt][e & 1] += dpre;
-          acc[nt][e] = dpre;
-        }
-        uint32_t h0, l0, h1, l1;
-        split_pair(acc[nt][0], acc[nt][1], h0, l0);  // row g
-        split_pair(acc[nt][2], acc[nt][3], h1, l1);  // row g + 8
-        const int col = 8 * nt + 2 * t;
-        *reinterpret_cast<uint32_t*>(dp_hi + g * TS + col) = h0;
-        *reinterpret_cast<uint32_t*>(dp_lo + g * TS + col) = l0;
-        *reinterpret_cast<uint32_t*>(dp_hi + (g + 8) * TS + col) = h1;
-        *reinterpret_cast<uint32_t*>(dp_lo + (g + 8) * TS + col) = l1;
-        // accumulator fragment -> A fragment of the dEnc product (k-tile nt/2, halves by nt parity)
-        da_hi[nt / 2][2 * (nt & 1) + 0] = h0; da_hi[nt / 2][2 * (nt & 1) + 1] = h1;
-        da_lo[nt / 2][2 * (nt & 1) + 0] = l0; da_lo[nt / 2][2 * (nt & 1) + 1] = l1;
-      }
-      // dEnc (16 x K0) = dPre1 (16 x H) . W1 (H x K0); B[k = j][n = kenc] = W1^T planes [kenc][j]
-#pragma unroll
-      for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-        dacc[nt2][0] = dacc[nt2][1] = dacc[nt2][2] = dacc[nt2][3] = 0.0f;
-#pragma unroll
-        for (int kt2 = 0; kt2 < H / 16; ++kt2) {
-          const int off = (8 * nt2 + g) * TS + 16 * kt2 + 2 * t;
-          const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(wt_hi + off), bh1 = *reinterpret_cast<const uint32_t*>(wt_hi + off + 8);
-          const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(wt_lo + off), bl1 = *reinterpret_cast<const uint32_t*>(wt_lo + off + 8);
-          mma_bf16_16816(dacc[nt2], da_lo[kt2], bh0, bh1);
-          mma_bf16_16816(dacc[nt2], da_hi[kt2], bl0, bl1);
-          mma_bf16_16816(dacc[nt2], da_hi[kt2], bh0, bh1);
-        }
-      }
-    }
-    __syncwarp();
-    // dW1 (H x K0) += dPre1^T (H x 16) . enc (16 x K0), operands transposed on the way out of shared memory
-    {
-      const int lm = lane >> 3, lr = lane & 7;
-      uint32_t bh[K0 / 16][4], bl[K0 / 16][4];  // per pair of 8-column blocks: {b0, b1} of the first, {b0, b1} of the second
-#pragma unroll
-      for (int np = 0; np < K0 / 16; ++np) {
-        const int off = (8 * (lm & 1) + lr) * WS + 8 * (2 * np + (lm >> 1));
-        ldmatrix_x4_trans(bh[np], e_hi + off);
-        ldmatrix_x4_trans(bl[np], e_lo + off);
-      }
-#pragma unroll
-      for (int jt = 0; jt < H / 16; ++jt) {
-        uint32_t ah[4], al[4];
-        const int off = (8 * (lm >> 1) + lr) * TS + 16 * jt + 8 * (lm & 1);
-        ldmatrix_x4_trans(ah, dp_hi + off);
-        ldmatrix_x4_trans(al, dp_lo + off);
-#pragma unroll
-        for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-          float4 c4 = wacc_s[32 * (jt * (K0 / 8) + nt2)];
-          float c[4] = {c4.x, c4.y, c4.z, c4.w};
-          const uint32_t h0 = bh[nt2 >> 1][2 * (nt2 & 1)], h1 = bh[nt2 >> 1][2 * (nt2 & 1) + 1];
-          const uint32_t l0 = bl[nt2 >> 1][2 * (nt2 & 1)], l1 = bl[nt2 >> 1][2 * (nt2 & 1) + 1];
-          mma_bf16_16816(c, al, h0, h1);
-          mma_bf16_16816(c, ah, l0, l1);
-          mma_bf16_16816(c, ah, h0, h1);
-          wacc_s[32 * (jt * (K0 / 8) + nt2)] = make_float4(c[0], c[1], c[2], c[3]);
-        }
-      }
-    }
-    __syncwarp();
-    // fused scatter: this lane holds dEnc of level 4*nt2 + t, its pair partner (t ^ 1) the neighbouring level.  The
-    // (level of the pair, row of the tile) combinations run as a real loop: fully unrolled the scatter alone was ~60 KB of
-    // SASS and the warps stalled on instruction fetch (ncu: stall_no_instruction 1.3 per issue with 12 warps per SM)
-    const int b0 = t & 1;
-#pragma unroll
-    for (int nt2 = 0; nt2 < K0 / 8; ++nt2) {
-      float pv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) pv[e] = __shfl_xor_sync(0xffffffffu, dacc[nt2][e], 1);
-#pragma unroll 1
-      for (int wr = 0; wr < 4; ++wr) {
-        const int which = wr >> 1, rr = wr & 1;    // which: the pair's even / odd level; rr: rows g / g + 8 of the m-tile
-        const bool mine = (which == b0);
-        const LevelDev lv = lvs[4 * nt2 + (t & ~1) + which];
-        float* tbl = grad_tables + lv.offset;
-        const bool live = (rr ? r_hi : r_lo) < n;
-        const float g0 = mine ? (rr ? dacc[nt2][2] : dacc[nt2][0]) : (rr ? pv[2] : pv[0]);
-        const float g1 = mine ? (rr ? dacc[nt2][3] : dacc[nt2][1]) : (rr ? pv[3] : pv[1]);
-        float xr[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) xr[d] = rr ? xv_hi[d] : xv_lo[d];
-        const Cell<D> cell = make_cell<D>(xr, lv);
-        const float w0 = b0 ? cell.wu[0] : cell.wl[0];
-        float v0 = g0 * w0, v1 = g1 * w0;
-        bool active = live;
-        if (nt2 < MERGE_NT2) {
-          // coarse levels of a locality-ordered batch: duplicates along the axis-0 line are summed in registers
-          const MergedHalf mh = merge_line_runs(cell.lo[0] + static_cast<uint32_t>(b0), v0, v1, live, rr ? line_mask[1] : line_mask[0], lane);
-          v0 = mh.v0; v1 = mh.v1; active = mh.active;
-        }
-        if (active) scatter_half_level_weighted<D>(cell, b0, lv, tbl, v0, v1);
-      }
-    }
-  }
-
-  // ---- flush ----
-  __syncthreads();
-  // dW1: sum of the warps' accumulators; element (j, k) sits at fragment position (jt, nt2, lane', c)
-  for (int e = threadIdx.x; e < H * K0; e += blockDim.x) {
-    const int j = e / K0, k = e - j * K0;
-    const int jt = j >> 4, jr = j & 15, nt2 = k >> 3, kc = k & 7;
-    const int idx = ((jt * (K0 / 8) + nt2) * 32 + 4 * (jr & 7) + (kc >> 1)) * 4 + 2 * (jr >> 3) + (kc & 1);
-    float sum = 0.0f;
-#pragma unroll
-    for (int w = 0; w < BWD_WARPS; ++w) sum += wacc_all[w * H * K0 + idx];
-    red_add_f32(gw1 + e, sum);
-  }
-  // column partials: sum over the 8 row groups (lanes with equal t), then one atomic per warp and column
-#pragma unroll
-  for (int nt = 0; nt < H / 8; ++nt)
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      float vb = pb1[nt][q], vw = pw2[nt][q];
-#pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        vb += __shfl_xor_sync(0xffffffffu, vb, o);
-        vw += __shfl_xor_sync(0xffffffffu, vw, o);
-      }
-      if (g == 0) {
-        red_add_f32(gb1 + 8 * nt + 2 * t + q, vb);
-        red_add_f32(gw2 + 8 * nt + 2 * t + q, vw);
-      }
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) pb2 += __shfl_xor_sync(0xffffffffu, pb2, o);
-  if (lane == 0) red_add_f32(gb2, pb2);
-}
-
-template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
-int launch_fused_bwd(const float* enc, int64_t n, const float* w1, const float* b1, const float* w2, const float* pre2,
-                     const float* gy, int act2, const float* x, const LevelTable& T, float* grad_tables, float* gw1, float* gb1,
-                     float* gw2, float* gb2, cudaStream_t s) {
-  constexpr size_t smem = fused_bwd_smem_bytes<K0, H>();
-  auto kernel = hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, CONTIGUOUS>;
-  static DeviceCache resident_cache;  // resident blocks of this kernel on the current device (one persistent wave)
-  const int dev = DeviceCache::device();
-  int resident = resident_cache.slot[dev].load(std::memory_order_acquire);
-  if (resident == 0) {
-    MRI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    MRI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BWD_THREADS, smem));
-    resident = (per_sm > 0 ? per_sm : 1) * sm_count();
-    resident_cache.slot[dev].store(resident, std::memory_order_release);
-  }
-  int64_t blocks = ((n + 15) / 16 + BWD_WARPS - 1) / BWD_WARPS;
-  if (blocks > resident) blocks = resident;
-  kernel<<<static_cast<int>(blocks), BWD_THREADS, smem, s>>>(enc, n, w1, b1, w2, pre2, gy, act2, x, T, grad_tables, gw1, gb1,
-                                                             gw2, gb2);
-  MRI_LAUNCH_OK("hashdecoder_mma_bwd_kernel");
-  return MRI_OK;
-}
-
-}  // namespace
-}  // namespace mri
+// encoding.py:127-128), for F = 2, L = 4 / 8 / 16 (K0 = 8 / 16 / 32), H = 64 / 128, D = 3 / 4.  Kernel template in
+// hashdecoder_bwd_impl.cuh; this file holds the headline geometry (L = 16, H = 64) and the C entry points.
+#include "hashdecoder.cuh"
+#include "hashdecoder_bwd_impl.cuh"
 
 using namespace mri;
 
@@ -346,8 +15,8 @@ extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, cons
   if (n == 0) return MRI_OK;
   if (!x || !enc || !w1 || !b1 || !w2 || !pre2 || !grad_y || !grad_tables || !host_levels || !grad_w1 || !grad_b1 || !grad_w2 || !grad_b2)
     return fail(MRI_ERR_INVALID, "hashdecoder_backward: null pointer");
-  if (n_features != 2 || k0 != 2 * n_levels || k0 != 32 || h != 64 || (act1 != MRI_ACT_GELU && act1 != MRI_ACT_RELU) || dim < 3 || dim > 4)
-    return fail(MRI_ERR_UNSUPPORTED, "hashdecoder_backward: fused kernel covers F=2, L=16, H=64, dim 3/4, GELU/ReLU "
+  if (k0 != 2 * n_levels || !fused_geometry_supported(dim, n_levels, n_features, h, act1))
+    return fail(MRI_ERR_UNSUPPORTED, "hashdecoder_backward: fused kernel covers F=2, L=4/8/16, H=64/128, dim 3/4, GELU/ReLU "
                                      "(got F=%d L=%d H=%d dim=%d act=%d)", n_features, n_levels, h, dim, act1);
   const uintptr_t need = dim == 4 ? 15 : 3;
   if ((reinterpret_cast<uintptr_t>(x) & need) || (reinterpret_cast<uintptr_t>(grad_tables) & 15) || (reinterpret_cast<uintptr_t>(enc) & 15))
@@ -365,7 +34,10 @@ extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, cons
     const int v = e ? atoi(e) : 8;
     return v <= 0 ? 0 : v <= 4 ? 1 : 2;
   }();
-#define CALL(DV, ACTV, MV, CV) launch_fused_bwd<DV, 32, 64, ACTV, MV, CV>(enc, n, w1, b1, w2, pre2, grad_y, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2, grad_b2, s)
+  if (!fused_geometry_is_headline(n_levels, h))
+    return launch_fused_bwd_geo(enc, n, dim, k0, h, w1, b1, w2, pre2, grad_y, act1, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2,
+                                grad_b2, merge_nt2, s);
+#define CALL(DV, ACTV, MV, CV) launch_fused_bwd<DV, 32, 64, ACTV, MV, CV>(enc, n, w1, b1, w2, pre2, grad_y, ACTV, act2, x, T, grad_tables, grad_w1, grad_b1, grad_w2, grad_b2, s)
 #define CALL_M(DV, ACTV) (merge_nt2 == 0 ? CALL(DV, ACTV, 0, true) : merge_nt2 == 1 ? CALL(DV, ACTV, 1, true) : CALL(DV, ACTV, 2, true))
   if (dim == 4 && act1 == MRI_ACT_GELU) return CALL_M(4, MRI_ACT_GELU);
   if (dim == 4 && act1 == MRI_ACT_RELU) return CALL_M(4, MRI_ACT_RELU);
@@ -376,5 +48,5 @@ extern "C" int mri_hashdecoder_backward(const float* x, int64_t n, int dim, cons
 }
 
 extern "C" int mri_hashdecoder_supported(int dim, int n_levels, int n_features, int h, int act1) {
-  return (n_features == 2 && n_levels == 16 && h == 64 && (dim == 3 || dim == 4) && (act1 == MRI_ACT_GELU || act1 == MRI_ACT_RELU)) ? 1 : 0;
+  return fused_geometry_supported(dim, n_levels, n_features, h, act1) ? 1 : 0;
 }

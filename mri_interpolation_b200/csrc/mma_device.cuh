@@ -25,16 +25,26 @@ __device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint3
 
 constexpr int MMA_PAD = 8;  // bf16 elements of row padding: conflict-free 32-bit fragment loads
 
-// W (rows x cols, fp32, row-major in global) -> two padded bf16 planes in shared memory
-template <int ROWS, int COLS>
+// W (rows x cols, fp32, row-major in global) -> two padded bf16 planes in shared memory.  KP >= COLS: column count the
+// untransposed planes are laid out for (row stride KP + MMA_PAD, columns COLS .. KP-1 zero) when the product runs on
+// more k columns than the matrix has (K0 = 8 inside one 16-wide mma k-tile).
+template <int ROWS, int COLS, int KP = COLS>
 __device__ __forceinline__ void stage_planes(const float* __restrict__ w, __nv_bfloat16* hi, __nv_bfloat16* lo, bool transpose) {
   for (int e = threadIdx.x; e < ROWS * COLS; e += blockDim.x) {
     const int r = e / COLS, c = e - r * COLS;
     const float v = __ldg(w + e);
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const int dst = transpose ? (c * (ROWS + MMA_PAD) + r) : (r * (COLS + MMA_PAD) + c);
+    const int dst = transpose ? (c * (ROWS + MMA_PAD) + r) : (r * (KP + MMA_PAD) + c);
     hi[dst] = h;
     lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+  if constexpr (KP > COLS) {
+    if (!transpose)
+      for (int e = threadIdx.x; e < ROWS * (KP - COLS); e += blockDim.x) {
+        const int r = e / (KP - COLS), c = COLS + e - r * (KP - COLS);
+        hi[r * (KP + MMA_PAD) + c] = __float2bfloat16_rn(0.0f);
+        lo[r * (KP + MMA_PAD) + c] = __float2bfloat16_rn(0.0f);
+      }
   }
 }
 

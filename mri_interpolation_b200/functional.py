@@ -37,6 +37,8 @@ def grad_write_epoch() -> int:
 
 def _direct_grad(p: torch.Tensor) -> Optional[torch.Tensor]:
     global _grad_write_epoch
+    if not p.is_leaf:  # e.g. a spectral-norm parametrised weight: autograd carries the gradient on to its leaves
+        return None
     g = getattr(p, "grad", None)
     if g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape:
         _grad_write_epoch += 1

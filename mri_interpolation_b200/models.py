@@ -287,6 +287,11 @@ class HashMLP(BaseMLP):
     ``base_resolution`` int -> ``MultiResHashGrid``; sequence -> ``MultiResHashGridV2`` (:691-708).
     ``batch_norm=True`` reproduces the shipped decoder blocks Linear -> BatchNorm1d -> activation ->
     Dropout (:718-739); ``batch_norm=False`` is the notebook's Linear -> activation variant (nb cell 37).
+    ``spectral_norm=True`` is the legacy recipe (legacy_code/hash_experimentation.py:213-234, the block the shipped
+    file keeps commented at :720-730): every Linear wrapped in ``torch.nn.utils.parametrizations.spectral_norm(...,
+    n_power_iterations=4, eps=1e-12, dim=None)``; the power iteration and W / sigma stay torch's (two matrix-vector
+    products on a 64 x 32 weight), the Linear itself runs on this package's dense kernel with the normalised weight;
+    ``weight_decay`` (legacy: 1e-5, L2-coupled Adam, :244-246) goes to the fused Adam kernel.
     ``n_layers`` reaches BaseMLP through **kwargs exactly like the reference (default 8).
     """
 
@@ -305,8 +310,12 @@ class HashMLP(BaseMLP):
                  lr: float = 1e-4,
                  *args,
                  batch_norm: bool = True,
+                 spectral_norm: bool = False,
+                 weight_decay: float = 0.0,
                  **kwargs):
         super().__init__(*args, **kwargs)
+        self.spectral_norm = spectral_norm
+        self.weight_decay = weight_decay
         self.dim_in = dim_in
         self.n_levels = n_levels
         self.n_features_per_level = n_features_per_level
@@ -340,13 +349,22 @@ class HashMLP(BaseMLP):
         for i in range(self.n_layers):
             in_features = self.encoding_dim_out if i == 0 else self.dim_hidden
             out_features = self.dim_out if i == (self.n_layers - 1) else self.dim_hidden
-            mods = [torch.nn.Linear(in_features=in_features, out_features=out_features)]
+            lin = torch.nn.Linear(in_features=in_features, out_features=out_features)
+            if spectral_norm:
+                lin = torch.nn.utils.parametrizations.spectral_norm(lin, n_power_iterations=4, eps=1e-12, dim=None)
+            mods = [lin]
             if batch_norm:
                 mods.append(torch.nn.BatchNorm1d(num_features=out_features))
             mods.append(activation())
             if batch_norm:
                 mods.append(torch.nn.Dropout(p=dropout, inplace=False))
             self.decoder.append(torch.nn.Sequential(*mods))
+
+    def configure_optimizers(self):
+        # models.py:68-70; the legacy recipe's Adam(weight_decay=1e-5) (legacy_code/hash_experimentation.py:244-246) when asked
+        sync_batchnorm_(self)
+        self.optimizer = FusedAdam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        return self.optimizer
 
     @staticmethod
     def _run_block(block, x):
@@ -364,7 +382,9 @@ class HashMLP(BaseMLP):
         return x
 
     def _fused_decoder_plan(self):
-        """(lin1, lin2, act1, act2) when the decoder is two Linear+activation blocks that csrc/decoder.cu fuses."""
+        """(lin1, lin2, act1, act2) when the decoder is two Linear+activation blocks with one output: the shape the
+        stand-alone fused decoder (csrc/decoder.cu, K0 in {16,32,64}, H in {32,64}) and / or the encoder+decoder kernels
+        (csrc/hashdecoder_*.cu, F = 2, L in {4,8,16}, H in {64,128}) cover; each caller checks its own kernel's geometry."""
         plan = self.__dict__.get("_decoder_plan", 0)
         if plan != 0:
             return plan
@@ -377,14 +397,14 @@ class HashMLP(BaseMLP):
             if ok:
                 l1, l2 = blocks[0][0], blocks[1][0]
                 a1, a2 = _fusable_activation(blocks[0][1]), _fusable_activation(blocks[1][1])
-                if l2.out_features == 1 and Fn.decoder2_supported(l1.in_features, l1.out_features, a1):
+                if l2.out_features == 1 and l2.in_features == l1.out_features and a1 in (ACT_GELU, ACT_RELU):
                     plan = (l1, l2, a1, a2)
         self.__dict__["_decoder_plan"] = plan
         return plan
 
     def decode(self, z):
         plan = self._fused_decoder_plan() if z.is_cuda else None
-        if plan is not None:
+        if plan is not None and Fn.decoder2_supported(plan[0].in_features, plan[0].out_features, plan[2]):
             l1, l2, a1, a2 = plan
             return Fn.Decoder2Fn.apply(z, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
         for block in self.decoder:
