@@ -265,7 +265,7 @@ class SirenNet(BaseMLP):
             self.__dict__["_tc_eligible"] = ok
         if not ok:
             if mode in ("bf16x3", "bf16"):
-                raise RuntimeError("this SirenNet does not fit the tensor-core tiles (hidden width % 128 != 0)")
+                raise RuntimeError("this SirenNet does not fit the tensor-core tiles (equal hidden widths >= 160, or a multiple of 128, are needed)")
             return None
         return "bf16x3" if mode == "auto" else mode
 

@@ -9,6 +9,11 @@ Backward mirrors it: dPre planes flow through dgrad GEMMs (W^T planes, epilogue 
 activation derivative), weight gradients are split-K tcgen05 GEMMs over the batch (MN-major operands).
 
 ``precision``: "bf16x3" = split-precision 3-MMA mode (fp32 parity, <= 1e-3), "bf16" = single MMA.
+
+Hidden widths that are not a multiple of the 128-wide tiles (the notebook's 4 x 352 SIREN, nb:837) run on the same
+kernels zero-padded to the next multiple of 128: padded units have zero weights and bias, so they output sin(0) = 0,
+contribute nothing downstream and receive exactly zero gradient - the result is that of the unpadded network, at
+(H_pad / H)^2 of its flops (1.19x for 352 -> 384) instead of the fp32 CUDA-core GEMM's ~15x lower rate.
 """
 from __future__ import annotations
 
@@ -21,6 +26,27 @@ from . import functional as Fn
 from ._lib import ACT_IDENTITY, ACT_SINE, MriB200Error
 
 PASSES = {"bf16x3": 3, "bf16": 1}
+TILE = 128
+MIN_PADDED_WIDTH = 160  # below this the padding overhead (H_pad / H)^2 exceeds 2.5x: the fp32 path keeps narrow nets
+
+
+def padded_width(h: int) -> int:
+    """Width the tensor-core tiles run at for a hidden width h (h itself when it already fits)."""
+    if h % TILE == 0:
+        return h
+    return (h + TILE - 1) // TILE * TILE if h >= MIN_PADDED_WIDTH else 0
+
+
+def _pad2(t: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = torch.zeros((rows, cols), device=t.device, dtype=t.dtype)
+    out[: t.shape[0], : t.shape[1]] = t
+    return out
+
+
+def _pad1(t: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros((n,), device=t.device, dtype=t.dtype)
+    out[: t.shape[0]] = t
+    return out
 
 
 def eligible(net) -> bool:
@@ -34,7 +60,10 @@ def eligible(net) -> bool:
             return False
         if i >= 1:
             m, k = l.weight.shape
-            if not (tc.supported(k, m) and tc.supported(m, k) and tc.wgrad_supported(k, m)):
+            if m != k or m != layers[0].weight.shape[0]:
+                return False
+            hp = padded_width(m)
+            if hp == 0 or not (tc.supported(hp, hp) and tc.wgrad_supported(hp, hp)):
                 return False
     last = net.last_layer
     if layers[0].weight.shape[1] > 4 or last.weight.shape[0] > 4:
@@ -58,6 +87,14 @@ class SirenTcFn(torch.autograd.Function):
         if d_in > 4 or m_out > 4:
             raise MriB200Error("tensor-core SIREN path handles dim_in <= 4 and dim_out <= 4; use precision='fp32'")
         three = passes == 3
+        h_real = h_dim
+        h_dim = padded_width(h_real)
+        if h_dim == 0:
+            raise MriB200Error(f"hidden width {h_real} does not fit the tensor-core tiles; use precision='fp32'")
+        if h_dim != h_real:  # zero-padded copies of this step's parameters (a few hundred KB; the planes are re-split anyway)
+            with torch.no_grad():
+                ws = [_pad2(ws[0], h_dim, d_in)] + [_pad2(w, h_dim, h_dim) for w in ws[1:-1]] + [_pad2(ws[-1], m_out, h_dim)]
+                bs = [_pad1(b, h_dim) for b in bs[:-1]] + [bs[-1]]
         # first layer (K = dim_in): planes written directly, no fp32 activations, no split pass
         a_hi = torch.empty((n, h_dim), device=dev, dtype=torch.bfloat16)
         a_lo = torch.empty_like(a_hi) if three else None
@@ -82,6 +119,7 @@ class SirenTcFn(torch.autograd.Function):
         if train:
             ctx.saved = (x2, acts, auxs, wplanes)
             ctx.params = params
+            ctx.padded = (ws, bs) if h_dim != h_real else None
             ctx.w0s, ctx.passes = w0s, passes
         ctx.train = train
         ctx.n_params = len(params)
@@ -97,6 +135,9 @@ class SirenTcFn(torch.autograd.Function):
         n_hidden = len(w0s)
         n = x2.shape[0]
         dev = x2.device
+        padded = ctx.padded
+        if padded is not None:  # the kernels see the zero-padded network; gradients are cut back to the real shapes below
+            ws, bs = padded
         h_dim, d_in = ws[0].shape
         m_out = ws[-1].shape[0]
         three = passes == 3
@@ -105,6 +146,9 @@ class SirenTcFn(torch.autograd.Function):
             d = Fn._direct_grad(p)
             direct.append(d is not None)
             grads.append(d if d is not None else torch.zeros_like(p))
+        real_grads = grads
+        if padded is not None:
+            grads = [torch.zeros_like(t) for pair in zip(ws, bs) for t in pair]
         gw, gb = grads[0::2], grads[1::2]
         gy = grad_y.reshape(n, m_out).contiguous()
         last = n_hidden - 1
@@ -129,6 +173,10 @@ class SirenTcFn(torch.autograd.Function):
             raise MriB200Error("tensor-core SIREN path needs at least two sine layers")
         _lib.call("mri_siren_first_backward", dpre0.data_ptr(), x2.data_ptr(), x2.stride(0), n, d_in, h_dim, gw[0].data_ptr(),
                   gb[0].data_ptr(), _lib.stream())  # dW0 and db0 in one pass over dPre0
+        if padded is not None:
+            for real, pad in zip(real_grads, grads):  # padded rows / columns hold exact zeros
+                real.add_(pad[: real.shape[0], : real.shape[1]] if real.dim() == 2 else pad[: real.shape[0]])
+            grads = real_grads
         out = [None if d else g for d, g in zip(direct, grads)]
         return (None, None, None) + tuple(out)
 

@@ -374,8 +374,11 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(gi, n_levels, hid
                 continue
             ref = params[name].grad
             scale = float(ref.abs().max()) + 1e-12
-            assert float((pf.grad.cpu() - ref).abs().max()) < 2e-3 * scale, (n, name)
-            assert float((pf.grad - pp.grad).abs().max()) < 2e-3 * scale, (n, name)
+            # ReLU: a pre-activation within rounding distance of 0 opens / closes its gate differently in the split
+            # bf16 product and in fp32 - isolated elements move by one sample's contribution, the norm bound below holds
+            tol = (5e-3 if act == "relu" else 2e-3) * scale
+            assert float((pf.grad.cpu() - ref).abs().max()) < tol, (n, name)
+            assert float((pf.grad - pp.grad).abs().max()) < tol, (n, name)
             if n >= 33:
                 assert rel_err(pf.grad, ref) < 1e-3, (n, name)
 
@@ -608,5 +611,7 @@ def test_hashmlp_spectral_norm_legacy_recipe_tracks_torch(batch_norm):
         assert rel_err(lv.embedding.weight, t) < 1e-3
     ref_sd, sd = ref_dec.state_dict(), net.decoder.state_dict()
     for k, v in ref_sd.items():
+        if batch_norm and k.endswith(".0.bias"):
+            continue  # a Linear bias in front of BatchNorm has zero true gradient: Adam amplifies rounding noise there
         if v.dtype.is_floating_point and v.numel() > 1:
             assert rel_err(sd[k], v) < 2e-3, k

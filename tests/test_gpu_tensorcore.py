@@ -101,9 +101,12 @@ def test_tc_dgrad_via_transposed_weights_and_mul_split():
 
 @pytest.mark.parametrize("kw,n", [(dict(dim_in=3, dim_hidden=256, n_layers=3), 3000),
                                   (dict(dim_in=4, dim_hidden=256, n_layers=5), 5000),
-                                  (dict(dim_in=3, dim_hidden=1024, n_layers=8), 4096)])
+                                  (dict(dim_in=3, dim_hidden=1024, n_layers=8), 4096),
+                                  (dict(dim_in=3, dim_hidden=352, n_layers=4), 3000),   # the notebook's SIREN (nb:837): 352 -> 384 tiles
+                                  (dict(dim_in=4, dim_hidden=200, n_layers=3), 1500)])  # 200 -> 256
 def test_sirennet_tensor_core_path_matches_oracle(kw, n):
-    """Whole network fwd + bwd in the split-precision mode vs the fp32 oracle: <= 1e-3 relative (north_star)."""
+    """Whole network fwd + bwd in the split-precision mode vs the fp32 oracle: <= 1e-3 relative (north_star); widths
+    that are not a multiple of 128 run zero-padded on the same tiles."""
     import torch.nn.functional as F
     from mri_interpolation_b200 import models
     from oracle import networks
