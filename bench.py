@@ -445,7 +445,8 @@ def red_rate_peak(dev):
     return out
 
 
-def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world, *, e2e=True, infer=True, kernels=True):
+def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world, *, e2e=True, infer=True, kernels=True,
+            settle_s=0.0):
     """One workload: timed training steps (+ sustained window with clocks), e2e, inference sweep, isolated kernels."""
     import torch.distributed as dist
     from mri_interpolation_b200 import _lib, sweep
@@ -507,6 +508,13 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
         step(i)
     for i in range(warmup):
         step(i)
+    if settle_s > 0:
+        # secondary legs (tens of steps): run untimed until the board has been under this load for ~settle_s, so the
+        # power-cap clock transient of the first second (SIREN legs draw ~1 kW) is not what the short timed region sees.
+        # The step count is agreed over the ranks first (the steps are collective).
+        ms5, _ = run_steps(0, 5)
+        n_settle = int(max_over_ranks(settle_s * 1e3 / max(ms5 / 5, 1e-3))) + 1
+        run_steps(0, min(n_settle, 2000))
     barrier()
     clocks.mark()
     launches0 = _lib.launch_count
@@ -766,6 +774,8 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
             "optimizer_step_ms": opt_step_ms,
             "roofline": roof, "kernels": kern, "infer": infer_line,
         }
+        if settle_s > 0:
+            line["config"]["untimed_settle_s_after_warmup"] = settle_s
         if kern and "adam_step" in kern:
             # what the gradient exchange adds to the optimiser step: in-step optimiser time minus the single-GPU Adam kernel
             line["exchange_exposed_ms"] = max(0.0, opt_step_ms - kern["adam_step"]["ms"]) if world > 1 else 0.0
@@ -796,7 +806,8 @@ def main():
                "sample": cpu_sample_text(kind, 2, args.cpu_batch_log2, dt)}
 
     # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT, in front of the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    # (from the environment or from an nccl.conf file, which only applies when the variable is unset)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = distributed.init_from_env("nccl")
     if not torch.cuda.is_available():
@@ -812,7 +823,7 @@ def main():
         for name in EXTRA_LEGS:
             steps = 20 if name == "siren_wide" else 40
             leg = run_leg(args, name, WORKLOADS[name][1], steps, 3, dev, rank, local_rank, world,
-                          e2e=False, infer=(name != "synthetic_hash"), kernels=True)
+                          e2e=False, infer=(name != "synthetic_hash"), kernels=True, settle_s=0.6)
             if rank == 0:
                 extra[name] = {k: leg[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "dtype", "data",
                                                    "config", "clocks", "sustained", "gpu_launches", "final_loss", "roofline", "kernels",

@@ -357,6 +357,18 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(gi, n_levels, hid
         assert any(lv.rows & (lv.rows - 1) for lv in levels)  # the non-power-of-two wrap is exercised
     for n in (1, 33, 5000):
         x, y = torch.rand(n, dim, generator=gen), torch.rand(n, 1, generator=gen)
+        if act == "relu":
+            # a pre-activation within rounding distance of the ReLU kink opens its gate in one summation order and not
+            # in the other (fp32 vs split bf16): such a sample moves 16 x 2^D table rows by its whole contribution, in
+            # ANY two implementations.  The comparison runs on samples whose gates are unambiguous.
+            with torch.no_grad():
+                tabs = [params[f"encoder.levels.{i}.embedding.weight"] for i in range(n_levels)]
+                pre1 = F.linear(networks.hashgrid.encode(x, tabs, levels, aniso), params["decoder.0.0.weight"], params["decoder.0.0.bias"])
+            keep = pre1.abs().min(dim=1).values > 1e-4
+            x, y = x[keep], y[keep]
+            n = x.shape[0]
+            if n == 0:
+                continue
         for p in params.values():
             p.grad = None
         F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, aniso, oact)).backward()
@@ -374,9 +386,7 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(gi, n_levels, hid
                 continue
             ref = params[name].grad
             scale = float(ref.abs().max()) + 1e-12
-            # ReLU: a pre-activation within rounding distance of 0 opens / closes its gate differently in the split
-            # bf16 product and in fp32 - isolated elements move by one sample's contribution, the norm bound below holds
-            tol = (5e-3 if act == "relu" else 2e-3) * scale
+            tol = 2e-3 * scale
             assert float((pf.grad.cpu() - ref).abs().max()) < tol, (n, name)
             assert float((pf.grad - pp.grad).abs().max()) < tol, (n, name)
             if n >= 33:
@@ -612,6 +622,7 @@ def test_hashmlp_spectral_norm_legacy_recipe_tracks_torch(batch_norm):
     ref_sd, sd = ref_dec.state_dict(), net.decoder.state_dict()
     for k, v in ref_sd.items():
         if batch_norm and k.endswith(".0.bias"):
-            continue  # a Linear bias in front of BatchNorm has zero true gradient: Adam amplifies rounding noise there
+            continue  # a Linear bias in front of BatchNorm has zero true gradient: Adam turns its rounding noise into +-lr steps
         if v.dtype.is_floating_point and v.numel() > 1:
-            assert rel_err(sd[k], v) < 2e-3, k
+            # ... and those bias steps feed the running means, hence the wider bound with BatchNorm
+            assert rel_err(sd[k], v) < (1e-2 if batch_norm else 2e-3), k
