@@ -364,7 +364,8 @@ def test_fused_hashdecoder_backward_matches_unfused_and_oracle(gi, n_levels, hid
             with torch.no_grad():
                 tabs = [params[f"encoder.levels.{i}.embedding.weight"] for i in range(n_levels)]
                 pre1 = F.linear(networks.hashgrid.encode(x, tabs, levels, aniso), params["decoder.0.0.weight"], params["decoder.0.0.bias"])
-            keep = pre1.abs().min(dim=1).values > 1e-4
+                pre2 = F.linear(F.relu(pre1), params["decoder.1.0.weight"], params["decoder.1.0.bias"])  # the output has a ReLU too
+            keep = (pre1.abs().min(dim=1).values > 1e-4) & (pre2.abs().min(dim=1).values > 1e-4)
             x, y = x[keep], y[keep]
             n = x.shape[0]
             if n == 0:
