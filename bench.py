@@ -858,8 +858,7 @@ def main():
                "sample": cpu_sample_text(kind, 2, args.cpu_batch_log2, dt)}
 
     # NCCL_DEBUG=VERSION (set in this image) makes NCCL print its version banner on STDOUT, in front of the one JSON line
-    # (from the environment or from an nccl.conf file, which only applies when the variable is unset)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = distributed.init_from_env("nccl")
     if not torch.cuda.is_available():
