@@ -578,6 +578,19 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
         barrier()
         opt_ms.append(a.elapsed_time(b))
     opt_step_ms = max_over_ranks(float(np.median(opt_ms[2:])))
+    exchange_parts = None
+    if world > 1 and getattr(opt, "sharded", False):
+        # where the exchange time goes: opening barrier (includes waiting for the slowest rank's backward), the fused
+        # reduce-scatter + Adam + all-gather kernel, closing barrier, local gradient clear (device times, median, max over ranks)
+        opt.time_exchange, opt.exchange_times = True, []
+        for i in range(12):
+            x, y = sampler.batch(index[i % ring])
+            model.training_step((x, y), i).backward()
+            opt.step()
+            opt.zero_grad()
+        opt.time_exchange = False
+        t = np.median(np.array(opt.exchange_times[2:]), axis=0)
+        exchange_parts = {k: max_over_ranks(float(v)) for k, v in zip(("open_barrier_ms", "kernel_ms", "close_barrier_ms", "clear_ms"), t)}
 
     # ---- e2e: host batches through the public API (PrefetchLoader + LightningModule.training_step + FusedAdam)
     # every step: H2D copy of that step's batch from pinned host memory (overlapped with the previous step's
@@ -823,7 +836,7 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
             "sustained": {"steps": more, "ms_per_step": sustained_ms_step, "value": n * world / (sustained_ms_step * 1e-3)},
             "e2e": e2e_line, "gpu_launches": launches, "final_loss": final_loss,
             "sampler_ms_per_batch": sampler_ms, "sampler": sampler_how,
-            "optimizer_step_ms": opt_step_ms,
+            "optimizer_step_ms": opt_step_ms, "exchange_parts": exchange_parts,
             "roofline": roof, "kernels": kern, "infer": infer_line,
         }
         if settle_s > 0:

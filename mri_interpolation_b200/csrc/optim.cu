@@ -5,6 +5,8 @@
 // clears the gradient in the same pass (saves the separate 4 B/param memset + one launch).
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mri {
@@ -118,46 +120,68 @@ __device__ __forceinline__ void multimem_st(float* mc_addr, const float4& v) {
                : "memory");
 }
 
+// U float4 per thread and iteration: all U gradient reductions (and the parameter / moment loads) are issued before the
+// first one is consumed, so a thread keeps U NVLink round trips in flight instead of one.
+template <int U>
 __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers, int world, int rank, float* __restrict__ m,
                                                            float* __restrict__ v, int64_t shard_begin4, int64_t shard_len4,
                                                            AdamArgs a) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < shard_len4; i += stride) {
-    const int64_t gi = shard_begin4 + i;  // float4 index inside the arena
-    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (peers.grad_mc) {
-      gg = multimem_ld_reduce_add(peers.grad_mc + 4 * gi);
-    } else {
+  AdamArgs b = a;
+  b.zero_grad = 0;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < shard_len4; i0 += stride * U) {
+    float4 gg[U], pp[U], mm[U], vv[U];
 #pragma unroll
-      for (int r = 0; r < MAX_PEERS; ++r) {
-        if (r < world) {
-          const float4 t = reinterpret_cast<const float4*>(peers.grad[r])[gi];
-          gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      gg[u] = zero;
+      if (i < shard_len4) {
+        const int64_t gi = shard_begin4 + i;  // float4 index inside the arena
+        if (peers.grad_mc) {
+          gg[u] = multimem_ld_reduce_add(peers.grad_mc + 4 * gi);
+        } else {
+#pragma unroll
+          for (int r = 0; r < MAX_PEERS; ++r) {
+            if (r < world) {
+              const float4 t = reinterpret_cast<const float4*>(peers.grad[r])[gi];
+              gg[u].x += t.x; gg[u].y += t.y; gg[u].z += t.z; gg[u].w += t.w;
+            }
+          }
         }
       }
     }
-    float4 pp = reinterpret_cast<const float4*>(peers.param[rank])[gi];
-    float4 mm = reinterpret_cast<float4*>(m)[i];
-    float4 vv = reinterpret_cast<float4*>(v)[i];
-    AdamArgs b = a;
-    b.zero_grad = 0;
-    adam_update(pp.x, gg.x, mm.x, vv.x, b);
-    adam_update(pp.y, gg.y, mm.y, vv.y, b);
-    adam_update(pp.z, gg.z, mm.z, vv.z, b);
-    adam_update(pp.w, gg.w, mm.w, vv.w, b);
-    reinterpret_cast<float4*>(m)[i] = mm;
-    reinterpret_cast<float4*>(v)[i] = vv;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (peers.param_mc) {
-      multimem_st(peers.param_mc + 4 * gi, pp);
-      if (a.zero_grad) multimem_st(const_cast<float*>(peers.grad_mc) + 4 * gi, zero);  // clears this slice on every rank
-    } else {
 #pragma unroll
-      for (int r = 0; r < MAX_PEERS; ++r)
-        if (r < world) {
-          reinterpret_cast<float4*>(peers.param[r])[gi] = pp;
-          if (a.zero_grad) reinterpret_cast<float4*>(const_cast<float*>(peers.grad[r]))[gi] = zero;
-        }
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < shard_len4) {
+        pp[u] = reinterpret_cast<const float4*>(peers.param[rank])[shard_begin4 + i];
+        mm[u] = reinterpret_cast<float4*>(m)[i];
+        vv[u] = reinterpret_cast<float4*>(v)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= shard_len4) continue;
+      const int64_t gi = shard_begin4 + i;
+      adam_update(pp[u].x, gg[u].x, mm[u].x, vv[u].x, b);
+      adam_update(pp[u].y, gg[u].y, mm[u].y, vv[u].y, b);
+      adam_update(pp[u].z, gg[u].z, mm[u].z, vv[u].z, b);
+      adam_update(pp[u].w, gg[u].w, mm[u].w, vv[u].w, b);
+      reinterpret_cast<float4*>(m)[i] = mm[u];
+      reinterpret_cast<float4*>(v)[i] = vv[u];
+      if (peers.param_mc) {
+        multimem_st(peers.param_mc + 4 * gi, pp[u]);
+        if (a.zero_grad) multimem_st(const_cast<float*>(peers.grad_mc) + 4 * gi, zero);  // clears this slice on every rank
+      } else {
+#pragma unroll
+        for (int r = 0; r < MAX_PEERS; ++r)
+          if (r < world) {
+            reinterpret_cast<float4*>(peers.param[r])[gi] = pp[u];
+            if (a.zero_grad) reinterpret_cast<float4*>(const_cast<float*>(peers.grad[r]))[gi] = zero;
+          }
+      }
     }
   }
 }
@@ -199,11 +223,16 @@ extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint
   a.grad_scale = static_cast<float>(grad_scale);
   a.zero_grad = zero_grad;  // the owner of a slice clears it in EVERY rank's gradient arena after reducing it
   const int64_t n4 = shard_len / 4;
-  int64_t want = (n4 + 255) / 256;
-  const int64_t cap = 8LL * sm_count();
+  // MRI_DP_UNROLL = 1 | 2 | 4 float4 per thread and iteration (default 2), MRI_DP_BLOCKS_PER_SM caps the grid (default 8)
+  static const int unroll = [] { const char* e = getenv("MRI_DP_UNROLL"); const int u = e ? atoi(e) : 2; return u >= 4 ? 4 : u <= 1 ? 1 : 2; }();
+  static const int per_sm = [] { const char* e = getenv("MRI_DP_BLOCKS_PER_SM"); const int u = e ? atoi(e) : 8; return u < 1 ? 1 : u > 16 ? 16 : u; }();
+  int64_t want = (n4 + 256LL * unroll - 1) / (256LL * unroll);
+  const int64_t cap = static_cast<int64_t>(per_sm) * sm_count();
   if (want > cap) want = cap;
-  adam_sharded_kernel<<<static_cast<int>(want), 256, 0, static_cast<cudaStream_t>(stream)>>>(peers, world, rank, m_shard, v_shard,
-                                                                                         shard_begin / 4, n4, a);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (unroll == 4) adam_sharded_kernel<4><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  else if (unroll == 2) adam_sharded_kernel<2><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  else adam_sharded_kernel<1><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
   MRI_LAUNCH_OK("adam_sharded_kernel");
   return MRI_OK;
 }

@@ -148,6 +148,9 @@ class FusedAdam(torch.optim.Optimizer):
             self.exp_avg = torch.zeros_like(self.arena.data)
             self.exp_avg_sq = torch.zeros_like(self.arena.data)
         self.step_count = 0
+        # measurement switch (bench.py): per-step device times of (opening barrier, exchange kernel, closing barrier, clear)
+        self.time_exchange = False
+        self.exchange_times = []
         self.grad_average = grad_average
         self.fuse_zero_grad = fuse_zero_grad
         # "the gradient arena is all zeros" is tracked with a token, not a guess: functional.grad_write_epoch() moves
@@ -269,18 +272,31 @@ class FusedAdam(torch.optim.Optimizer):
             world = self._world()
             self.step_count += 1
             remote_clear = bool(self._grad_mc) and _MULTICAST_CLEAR
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.time_exchange else None
+            if ev:
+                ev[0].record()
             self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
+            if ev:
+                ev[1].record()
             _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc, world,
                       dist.get_rank(self.process_group),
                       self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
                       float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
                       (1.0 / world) if self.grad_average else 1.0, 1 if remote_clear else 0, _lib.stream())
+            if ev:
+                ev[2].record()
             # new parameters landed everywhere and every slice of my gradient arena has been read by its owner
             self.arena.data_hdl.barrier(channel=1)
+            if ev:
+                ev[3].record()
             if not remote_clear:
                 # clearing remotely doubles the NVLink stores (P2P pointers: measured 1.265 vs 1.221 ms/step at W=2;
                 # multicast: every rank would receive a second arena's worth of zeros), so each rank clears its own arena
                 self.arena.grad.zero_()
+            if ev:
+                ev[4].record()
+                ev[4].synchronize()
+                self.exchange_times.append(tuple(ev[i].elapsed_time(ev[i + 1]) for i in range(4)))
             self.allreduce_count += 1
             self._grads_clean = True
             return loss
