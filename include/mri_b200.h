@@ -240,6 +240,16 @@ int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_
                           double lr, double beta1, double beta2, double eps, double weight_decay,
                           double grad_scale, int zero_grad, void* stream);
 
+/* Same step with the two cross-rank barriers folded into the kernel: host_peer_flags[r] = device pointer of rank r's
+ * 32-int flag buffer (P2P-mapped symmetric memory, zero-initialised once).  The kernel waits until every rank's
+ * gradients are complete before touching them and does not complete on the stream before every rank has stored its
+ * shard everywhere - no separate barrier launches.  `step` must be the same on all ranks and grow by one per call. */
+int mri_adam_step_sharded_sync(const uint64_t* host_peer_grads, const uint64_t* host_peer_params,
+                               uint64_t grad_multicast, uint64_t param_multicast, const uint64_t* host_peer_flags,
+                               int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin,
+                               int64_t shard_len, int64_t step, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, double grad_scale, int zero_grad, void* stream);
+
 /* ---- dense-grid sweep -------------------------------------------------------------------- */
 
 /* Coordinates of voxels [first, first+count) of a C-order grid of `shape` (launcher.py:191-202,

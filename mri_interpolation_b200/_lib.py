@@ -55,6 +55,9 @@ SIGNATURES = {
     "mri_adam_step_sharded": [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_uint64,
                               _I, _I, _P, _P, _I64, _I64, _I64,
                               _D, _D, _D, _D, _D, _D, _I, _P],
+    "mri_adam_step_sharded_sync": [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_uint64, ctypes.c_uint64,
+                                   ctypes.POINTER(ctypes.c_uint64), _I, _I, _P, _P, _I64, _I64, _I64,
+                                   _D, _D, _D, _D, _D, _D, _I, _P],
     "mri_grid_coords": [_P, ctypes.POINTER(ctypes.c_int32), _I, _I64, _I64, _P, _P],
     "mri_gather_voxels": [_P, ctypes.POINTER(ctypes.c_int32), _I, _P, _I64, _P, _P, _P, _P],
     "mri_hashmlp_sweep": [_P, ctypes.POINTER(ctypes.c_int32), _I, _I64, _I64, _P, ctypes.POINTER(Level), _I, _I, _P,

@@ -105,7 +105,28 @@ struct PeerPtrs {
   float* param[MAX_PEERS];
   const float* grad_mc;  // NVSwitch multicast mapping of the gradient arenas (0 = not available)
   float* param_mc;       // NVSwitch multicast mapping of the parameter arenas
+  int* flags[MAX_PEERS]; // in-kernel cross-rank synchronisation (SYNC = true): per rank 32 ints of symmetric memory,
+                         // [0..7] "gradients of rank r are complete" and [8..15] "rank r has stored its shard everywhere"
+                         // (both hold the step number), [16] count of finished CTAs of the local launch
+  int step;
 };
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p >= want; a rank that never arrives ends the process (trap) after ~60 s instead of hanging the GPU
+__device__ __forceinline__ void wait_flag(const int* p, int want) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) < want) {
+    __nanosleep(64);
+    if (clock64() - t0 > 120000000000LL) __trap();
+  }
+}
 
 // in-switch (NVLS) reduction: one load returns the sum over every rank's copy of the address
 __device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc_addr) {
@@ -122,10 +143,21 @@ __device__ __forceinline__ void multimem_st(float* mc_addr, const float4& v) {
 
 // U float4 per thread and iteration: all U gradient reductions (and the parameter / moment loads) are issued before the
 // first one is consumed, so a thread keeps U NVLink round trips in flight instead of one.
-template <int U>
+//
+// SYNC = true folds the two cross-rank barriers into the kernel: CTA 0 publishes "my gradient arena is complete" (the
+// kernel runs after this rank's backward on the stream) to every peer, every CTA waits until all peers have published
+// theirs before it touches their arenas; at the end the last CTA to finish publishes "my shard is stored everywhere"
+// and does not retire before all peers have published the same - so when the kernel completes on the stream, every
+// replica holds all new parameters and every slice of the local gradient arena has been consumed by its owner.
+template <int U, bool SYNC>
 __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers, int world, int rank, float* __restrict__ m,
                                                            float* __restrict__ v, int64_t shard_begin4, int64_t shard_len4,
                                                            AdamArgs a) {
+  if constexpr (SYNC) {
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, peers.step);
+    if (threadIdx.x < world) wait_flag(peers.flags[rank] + threadIdx.x, peers.step);
+    __syncthreads();
+  }
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   AdamArgs b = a;
   b.zero_grad = 0;
@@ -184,6 +216,23 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
       }
     }
   }
+  if constexpr (SYNC) {
+    // one system fence per CTA, after the CTA barrier (the cooperative-groups grid-sync pattern: the barrier orders the
+    // other threads' stores before thread 0's fence).  A fence in every thread made the kernel 3.6x slower (0.42 vs
+    // 0.12 ms at W = 2): MEMBAR.SYS is serviced one at a time per SM.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      int* local = peers.flags[rank];
+      const int ticket = atomicAdd(local + 16, 1);
+      if (ticket == static_cast<int>(gridDim.x) - 1) {
+        local[16] = 0;  // every CTA of this launch has been counted: ready for the next launch
+        __threadfence_system();
+        for (int r = 0; r < world; ++r) st_release_sys(peers.flags[r] + 8 + rank, peers.step);
+        for (int r = 0; r < world; ++r) wait_flag(local + 8 + r, peers.step);
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -191,17 +240,50 @@ __global__ void __launch_bounds__(256) adam_sharded_kernel(const PeerPtrs peers,
 
 using namespace mri;
 
+namespace {
+int sharded_step(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast, uint64_t param_multicast,
+                 const uint64_t* host_peer_flags, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin,
+                 int64_t shard_len, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                 double grad_scale, int zero_grad, void* stream);
+}
+
 extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast,
                                      uint64_t param_multicast, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
                                      double lr, double beta1, double beta2, double eps, double weight_decay,
                                      double grad_scale, int zero_grad, void* stream) {
+  return sharded_step(host_peer_grads, host_peer_params, grad_multicast, param_multicast, nullptr, world, rank, m_shard, v_shard,
+                      shard_begin, shard_len, step, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grad, stream);
+}
+
+extern "C" int mri_adam_step_sharded_sync(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast,
+                                          uint64_t param_multicast, const uint64_t* host_peer_flags, int world, int rank,
+                                          float* m_shard, float* v_shard, int64_t shard_begin, int64_t shard_len, int64_t step,
+                                          double lr, double beta1, double beta2, double eps, double weight_decay,
+                                          double grad_scale, int zero_grad, void* stream) {
+  if (!host_peer_flags) return fail(MRI_ERR_INVALID, "adam_sharded_sync: null flag pointers");
+  if (step >= (int64_t{1} << 31)) return fail(MRI_ERR_INVALID, "adam_sharded_sync: step counter exceeds the 32-bit flag range");
+  return sharded_step(host_peer_grads, host_peer_params, grad_multicast, param_multicast, host_peer_flags, world, rank, m_shard,
+                      v_shard, shard_begin, shard_len, step, lr, beta1, beta2, eps, weight_decay, grad_scale, zero_grad, stream);
+}
+
+namespace {
+int sharded_step(const uint64_t* host_peer_grads, const uint64_t* host_peer_params, uint64_t grad_multicast, uint64_t param_multicast,
+                 const uint64_t* host_peer_flags, int world, int rank, float* m_shard, float* v_shard, int64_t shard_begin,
+                 int64_t shard_len, int64_t step, double lr, double beta1, double beta2, double eps, double weight_decay,
+                 double grad_scale, int zero_grad, void* stream) {
   if (!host_peer_grads || !host_peer_params || !m_shard || !v_shard) return fail(MRI_ERR_INVALID, "adam_sharded: null pointer");
   if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(MRI_ERR_UNSUPPORTED, "adam_sharded: world=%d rank=%d", world, rank);
   if (shard_begin < 0 || shard_len < 0 || (shard_begin & 3) || (shard_len & 3) || step < 1)
     return fail(MRI_ERR_INVALID, "adam_sharded: shard must be a multiple of 4 floats and step >= 1");
-  if (shard_len == 0) return MRI_OK;
+  if (shard_len == 0 && !host_peer_flags) return MRI_OK;
+  if (shard_len == 0) return fail(MRI_ERR_INVALID, "adam_sharded_sync: empty shard (every rank must take part in the flags)");
   PeerPtrs peers{};
+  peers.step = static_cast<int>(step);
   for (int r = 0; r < world; ++r) {
+    if (host_peer_flags) {
+      if (host_peer_flags[r] & 3) return fail(MRI_ERR_INVALID, "adam_sharded_sync: flag buffers must be 4-byte aligned");
+      peers.flags[r] = reinterpret_cast<int*>(host_peer_flags[r]);
+    }
     if ((host_peer_grads[r] | host_peer_params[r]) & 15) return fail(MRI_ERR_INVALID, "adam_sharded: peer arenas must be 16-byte aligned");
     peers.grad[r] = reinterpret_cast<const float*>(host_peer_grads[r]);
     peers.param[r] = reinterpret_cast<float*>(host_peer_params[r]);
@@ -230,12 +312,20 @@ extern "C" int mri_adam_step_sharded(const uint64_t* host_peer_grads, const uint
   const int64_t cap = static_cast<int64_t>(per_sm) * sm_count();
   if (want > cap) want = cap;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (unroll == 4) adam_sharded_kernel<4><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
-  else if (unroll == 2) adam_sharded_kernel<2><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
-  else adam_sharded_kernel<1><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  if (host_peer_flags) {
+    // every CTA spins on the peers' flags at its start: the grid must be resident at once (<= 8 CTAs of 256 threads per SM)
+    const int64_t resident = 6LL * sm_count();
+    if (want > resident) want = resident;
+    if (unroll == 4) adam_sharded_kernel<4, true><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+    else if (unroll == 2) adam_sharded_kernel<2, true><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+    else adam_sharded_kernel<1, true><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  } else if (unroll == 4) adam_sharded_kernel<4, false><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  else if (unroll == 2) adam_sharded_kernel<2, false><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
+  else adam_sharded_kernel<1, false><<<static_cast<int>(want), 256, 0, s>>>(peers, world, rank, m_shard, v_shard, shard_begin / 4, n4, a);
   MRI_LAUNCH_OK("adam_sharded_kernel");
   return MRI_OK;
 }
+}  // namespace
 
 extern "C" int mri_mse_loss_grad(const float* pred, const float* target, int64_t count, float inv_count,
                                  float* grad_pred, float* loss, void* stream) {

@@ -144,6 +144,18 @@ class FusedAdam(torch.optim.Optimizer):
             self._param_mc = int(getattr(self.arena.data_hdl, "multicast_ptr", 0) or 0) if use_mc else 0
             if not (self._grad_mc and self._param_mc):
                 self._grad_mc = self._param_mc = 0
+            # in-kernel synchronisation (csrc/optim.cu, SYNC = true; opt-in with MRI_DP_INKERNEL_SYNC=1): the two
+            # symmetric-memory barrier launches around the exchange kernel become flag stores / polls inside it.  Measured
+            # at W = 2: 0.804 vs 0.800 ms/step - the barrier launches cost nothing beyond the wait for the slowest rank, which
+            # the kernel now does itself (profiles/r02_exchange_ab_w8.txt) - so the default stays the barrier launches.
+            self._peer_flags = None
+            if os.environ.get("MRI_DP_INKERNEL_SYNC", "0") == "1":
+                import torch.distributed._symmetric_memory as symm
+                self._flags = symm.empty(32, dtype=torch.int32, device=self.arena.data.device)
+                self._flags.zero_()
+                self._flags_hdl = symm.rendezvous(self._flags, group)
+                self._flags_hdl.barrier(channel=2)  # every rank's flags are zero before anyone's first step
+                self._peer_flags = (ctypes.c_uint64 * world)(*[int(p) for p in self._flags_hdl.buffer_ptrs])
         else:
             self.exp_avg = torch.zeros_like(self.arena.data)
             self.exp_avg_sq = torch.zeros_like(self.arena.data)
@@ -275,18 +287,25 @@ class FusedAdam(torch.optim.Optimizer):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if self.time_exchange else None
             if ev:
                 ev[0].record()
-            self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
+            fused_sync = self._peer_flags is not None
+            if not fused_sync:
+                self.arena.grad_hdl.barrier(channel=0)  # every rank's backward has finished writing its gradient arena
             if ev:
                 ev[1].record()
-            _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc, world,
-                      dist.get_rank(self.process_group),
-                      self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
-                      float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                      (1.0 / world) if self.grad_average else 1.0, 1 if remote_clear else 0, _lib.stream())
+            args = (world, dist.get_rank(self.process_group),
+                    self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard_begin, self.shard_len, self.step_count,
+                    float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                    (1.0 / world) if self.grad_average else 1.0, 1 if remote_clear else 0, _lib.stream())
+            if fused_sync:
+                _lib.call("mri_adam_step_sharded_sync", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc,
+                          self._peer_flags, *args)
+            else:
+                _lib.call("mri_adam_step_sharded", self._peer_grads, self._peer_params, self._grad_mc, self._param_mc, *args)
             if ev:
                 ev[2].record()
             # new parameters landed everywhere and every slice of my gradient arena has been read by its owner
-            self.arena.data_hdl.barrier(channel=1)
+            if not fused_sync:
+                self.arena.data_hdl.barrier(channel=1)
             if ev:
                 ev[3].record()
             if not remote_clear:

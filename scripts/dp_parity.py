@@ -55,7 +55,7 @@ if rank == 0:
     single = sweep.dense_sweep(dp_model, shape).reshape(shape).cpu().numpy()
     ok_sweep = bool((single == full).all())
 res = {"world": world, "steps": steps, "global_batch": n_global, "max_rel_param_diff_vs_single_gpu": worst,
-       "max_abs_replica_diff": replica_diff, "allreduces": dp_opt.allreduce_count, "overlap": bool(overlap), "sharded_p2p_adam": bool(dp_opt.sharded), "multimem": bool(getattr(dp_opt, "_grad_mc", 0)), "sweep_slabs_tile_exactly": ok_sweep}
+       "max_abs_replica_diff": replica_diff, "allreduces": dp_opt.allreduce_count, "overlap": bool(overlap), "sharded_p2p_adam": bool(dp_opt.sharded), "multimem": bool(getattr(dp_opt, "_grad_mc", 0)), "inkernel_sync": getattr(dp_opt, "_peer_flags", None) is not None, "sweep_slabs_tile_exactly": ok_sweep}
 if rank == 0:
     print(json.dumps(res))
     out_dir = os.environ.get("MRI_DP_PARITY_OUT", os.path.join(ROOT, "gpurun_out"))

@@ -15,9 +15,11 @@ for line in open("gpurun_out/abx_$tag.json"):
         print("$tag: step %.4f ms  opt %.4f  exposed %.4f  parts %s" % (d["ms_per_step"], d["optimizer_step_ms"], d.get("exchange_exposed_ms") or 0, d.get("exchange_parts")))
 PY
 }
-run u2 MRI_DP_UNROLL=2
+run sync MRI_DP_INKERNEL_SYNC=1
+run barriers MRI_DP_INKERNEL_SYNC=0
+if [ "$2" == "all" ]; then
 run u1 MRI_DP_UNROLL=1
 run u4 MRI_DP_UNROLL=4
-run u2_b16 MRI_DP_UNROLL=2 MRI_DP_BLOCKS_PER_SM=16
-run u2_b4 MRI_DP_UNROLL=2 MRI_DP_BLOCKS_PER_SM=4
-run p2p_u2 MRI_DP_MULTIMEM=0 MRI_DP_UNROLL=2
+run p2p MRI_DP_MULTIMEM=0
+run mm MRI_DP_MULTIMEM=1
+fi

@@ -6,6 +6,8 @@ global batches up to summation order (scripts/dp_parity.py asserts 1e-4 relative
   * fused reduce-scatter + Adam + all-gather kernel over P2P pointers          (MRI_DP_MULTIMEM=0)
   * the same kernel on NVSwitch multimem.ld_reduce / multimem.st (what SCALE runs at N >= 4)   (MRI_DP_MULTIMEM=1)
   * NCCL all-reduce + full Adam                                                (MRI_DP_SHARDED=0)
+The fused kernel is bracketed by two symmetric-memory barrier launches (the default); the variant that synchronises the
+ranks itself (flag stores / polls in symmetric memory, MRI_DP_INKERNEL_SYNC=1) is covered too.
 and the ranks' dense-sweep slabs must tile the single-GPU sweep exactly."""
 import json
 import os
@@ -28,8 +30,10 @@ def _free_port() -> int:
 
 
 MODES = {
-    "sharded_p2p": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "0"},
-    "sharded_multimem": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "1"},
+    "sharded_p2p": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "0", "MRI_DP_INKERNEL_SYNC": "0"},
+    "sharded_multimem": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "1", "MRI_DP_INKERNEL_SYNC": "0"},
+    "sharded_p2p_inkernel_sync": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "0", "MRI_DP_INKERNEL_SYNC": "1"},
+    "sharded_multimem_inkernel_sync": {"MRI_DP_SHARDED": "1", "MRI_DP_MULTIMEM": "1", "MRI_DP_INKERNEL_SYNC": "1"},
     "nccl_allreduce": {"MRI_DP_SHARDED": "0", "MRI_DP_OVERLAP": "0"},
 }
 
@@ -46,9 +50,11 @@ def test_two_gpu_training_equals_single_gpu_training(mode, tmp_path):
     res = json.load(open(tmp_path / "dp_parity_w2.json"))
     assert res["world"] == 2 and res["max_abs_replica_diff"] == 0.0 and res["sweep_slabs_tile_exactly"]
     assert res["max_rel_param_diff_vs_single_gpu"] < 1e-5, res
-    if mode == "sharded_multimem":
+    if mode.startswith("sharded_multimem"):
         assert res["sharded_p2p_adam"] and res["multimem"], res  # the NVLS branch really ran
-    elif mode == "sharded_p2p":
+    elif mode.startswith("sharded_p2p"):
         assert res["sharded_p2p_adam"] and not res["multimem"], res
     else:
         assert not res["sharded_p2p_adam"], res
+    if mode.startswith("sharded"):
+        assert res["inkernel_sync"] == mode.endswith("inkernel_sync"), res
