@@ -399,7 +399,10 @@ def traffic_probe(args, batch_log2):
     for r in rows[1:]:
         if len(r) <= col["Metric Value"]:
             continue
-        kname = "hashdecoder_bwd" if "hashdecoder_mma_bwd" in r[col["Kernel Name"]] else "hashdecoder_fwd"
+        kn = r[col["Kernel Name"]]
+        # the one-kernel training step is the backward template with STEP = true (last template argument)
+        kname = ("hashmlp_step" if "(bool)1, (bool)1>" in kn else
+                 "hashdecoder_bwd" if "hashdecoder_mma_bwd" in kn else "hashdecoder_fwd")
         try:
             out.setdefault(kname, {})[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", ""))
         except ValueError:
@@ -415,9 +418,10 @@ def probe_main(args):
     opt = model.configure_optimizers()
     n = 1 << args.batch_log2
     index, _, _ = draw_index_ring(args.workload, sampler, info, n, 4, dev, 0, 1)
+    from mri_interpolation_b200.pl_compat import training_step_and_backward
     for i in range(args.probe_steps):
         x, y = sampler.batch(index[i % 4])
-        model.training_step((x, y), i).backward()
+        training_step_and_backward(model, (x, y), i)
         opt.step()
         opt.zero_grad()
     torch.cuda.synchronize()
@@ -499,10 +503,13 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
     ring = 32
     index, sampler_ms, sampler_how = draw_index_ring(name, sampler, info, n, ring, dev, rank, world)
 
+    from mri_interpolation_b200.pl_compat import training_step_and_backward
+
     def step(i):
+        # exactly what pl_compat.Trainer.fit runs per batch: training_step + backward (HashMLP under the MSE loss: ONE kernel
+        # for both, csrc/hashdecoder_step.cu; MRI_FUSED_STEP=0 restores forward kernel + MSE kernel + backward kernel)
         x, y = sampler.batch(index[i % ring])
-        loss = model.training_step((x, y), i)
-        loss.backward()
+        loss = training_step_and_backward(model, (x, y), i)
         opt.step()
         opt.zero_grad()
         return loss
@@ -571,7 +578,7 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
     opt_ms = []
     for i in range(12):
         x, y = sampler.batch(index[i % ring])
-        model.training_step((x, y), i).backward()
+        training_step_and_backward(model, (x, y), i)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); opt.step(); b.record()
         opt.zero_grad()
@@ -585,7 +592,7 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
         opt.time_exchange, opt.exchange_times = True, []
         for i in range(12):
             x, y = sampler.batch(index[i % ring])
-            model.training_step((x, y), i).backward()
+            training_step_and_backward(model, (x, y), i)
             opt.step()
             opt.zero_grad()
         opt.time_exchange = False
@@ -717,6 +724,10 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
                     fused_ms = timed(lambda: torch.autograd.backward(pred, gy, retain_graph=True))
                     fused_fwd_ms = timed(lambda: model(x))  # training forward: gather + decoder, enc and pre2 written
                 del pred
+            # the one-kernel training step (gather + decoder + MSE + decoder backward + scatter), when the model has it
+            step_ms = None
+            if getattr(model, "fused_training_step", None) is not None and model.fused_training_step((x, y), 0) is not None:
+                step_ms = timed(lambda: model.fused_training_step((x, y), 0))
             opt.arena.grad.zero_()
             # the single-GPU Adam kernel on scratch arenas of the model's size (the model itself is not stepped here)
             scratch = [torch.zeros(opt.arena.numel, device=dev) for _ in range(4)]
@@ -756,23 +767,38 @@ def run_leg(args, name, batch_log2, steps, warmup, dev, rank, local_rank, world,
                     red_sectors = NCU_RED_SECTORS["hashdecoder_bwd"]
                 else:
                     traffic_src = None
-            step_bytes = (2 * HASH_BYTES_PER_COORD + 8) * n + adam_bytes  # fused fwd + fused bwd + Adam, algorithmic
+            if step_ms is not None and fused_ms is not None:
+                # ONE kernel for forward + loss + backward: coords + target read, L*2^D*F*4 B gathered and as many reduced
+                fused_step_bytes = (4 * 4 + 4 + 2 * 16 * 16 * 2 * 4) * n
+                kern["hashmlp_step"] = {"ms": step_ms, "GBps_algorithmic": fused_step_bytes / step_ms / 1e6,
+                                        "frac": fused_step_bytes / step_ms / 1e6 / hbm_peak}
+                top, hash_bytes = "hashmlp_step", fused_step_bytes
+                if probe and top in probe and "dram__bytes_read.sum" in probe[top]:
+                    traffic = probe[top]["dram__bytes_read.sum"] + probe[top]["dram__bytes_write.sum"]
+                    red_sectors = probe[top].get("lts__t_sectors_srcunit_tex_op_red.sum")
+                else:
+                    traffic, traffic_src = None, f"none for the one-kernel step (live probe: {traffic_src})"
+                step_bytes = fused_step_bytes + adam_bytes
+            else:
+                step_bytes = (2 * HASH_BYTES_PER_COORD + 8) * n + adam_bytes  # fused fwd + fused bwd + Adam, algorithmic
             kern["whole_step"] = {"ms": ms_step, "algorithmic_GB": step_bytes / 1e9, "GBps_algorithmic": step_bytes / ms_step / 1e6,
                                   "frac": step_bytes / ms_step / 1e6 / hbm_peak}
             roof = {"kernel": top, "bound": "hbm", "achieved": kern[top]["GBps_algorithmic"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kern[top]["frac"], "traffic": traffic, "traffic_source": traffic_src if fused_ms is not None else None,
                     "peak_source": peak_src + " hbm_gbs", "algorithmic_bytes_per_launch": hash_bytes,
-                    "note": "2192 B/coord (4D + L*2^D*F*4 gathered-or-reduced + L*F*4 encoding) x coords per launch (+4 B/coord dy "
-                            "for the fused decoder-backward+scatter kernel, which also does 8.4 kMAC/coord of decoder math); "
+                    "note": "one-kernel training step: 4116 B/coord = 4D coords + target + L*2^D*F*4 gathered + L*F*2^D*4 reduced "
+                            "(the encoding never goes to memory); two-kernel path: 2192 B/coord per kernel (4D + L*2^D*F*4 "
+                            "gathered-or-reduced + L*F*4 encoding, +4 B/coord dy for the backward) and 8.4 kMAC/coord of decoder math; "
                             "traffic = ncu dram read+write per launch: the 61 MB of tables stay in the 126 MB L2, so DRAM moves "
                             "less than the algorithmic bytes - the kernels are bound by the L2 sector / L2 atomic rates "
                             "(DESIGN.md 3), not HBM"}
             if fused_ms is not None and red_sectors:
                 # the resource that actually binds the backward: 32-byte sector reductions retired by the L2 atomic units
                 peak = red_rate_peak(dev)
-                ach = red_sectors / (fused_ms * 1e-3) / 1e9
+                bind_ms = step_ms if top == "hashmlp_step" else fused_ms
+                ach = red_sectors / (bind_ms * 1e-3) / 1e9
                 roof["binding"] = {"resource": "L2 atomic units: 32-byte sector reductions (red.global.add.v2.f32)",
-                                   "kernel": "hashdecoder_bwd", "sector_ops_per_launch": red_sectors, "achieved": ach,
+                                   "kernel": top if top == "hashmlp_step" else "hashdecoder_bwd", "sector_ops_per_launch": red_sectors, "achieved": ach,
                                    "peak": peak["paired"], "peak_spread": peak["spread"], "unit": "G sector-ops/s",
                                    "frac": ach / peak["paired"],
                                    "peak_source": "measured in this run by mri_probe_red_rate (csrc/probe.cu): every warp instruction "

@@ -143,6 +143,20 @@ int mri_hashdecoder_forward(const float* x, int64_t n, int dim, const float* tab
                             const float* w2, const float* b2, int act1, int act2, float* enc, float* y, float* pre2,
                             void* stream);
 
+/* The WHOLE training step of HashMLP under the mean-squared-error loss in one kernel (BaseMLP.training_step
+ * models.py:61-66 = F.mse_loss(y, model(x)) on HashMLP.forward :741-744, plus the autograd of both): gather, decoder
+ * forward, loss, decoder backward and table scatter per 16-coordinate tile, nothing but the gradients written.
+ * target (n) regression targets; inv_count = 1 / (number of elements the mean runs over, normally n);
+ * *loss (device float, caller zero-fills) += sum (y - target)^2 * inv_count; y (n) optional predictions or NULL.
+ * Gradients accumulate into grad_tables (level layout host_grad_levels, which must equal host_levels' offsets and
+ * rows) and grad_w1 / grad_b1 / grad_w2 / grad_b2.  Headline geometry only (mri_hashmlp_mse_step_supported). */
+int mri_hashmlp_mse_step_supported(int dim, int n_levels, int n_features, int h, int act1);
+int mri_hashmlp_mse_step(const float* x, const float* target, int64_t n, int dim, const float* tables,
+                         const mri_level_t* host_levels, int n_levels, int n_features, int k0, int h,
+                         const float* w1, const float* b1, const float* w2, const float* b2, int act1, int act2,
+                         float inv_count, float* grad_tables, const mri_level_t* host_grad_levels, float* grad_w1,
+                         float* grad_b1, float* grad_w2, float* grad_b2, float* loss, float* y, void* stream);
+
 /* ---- wide SIREN layers on tcgen05 tensor cores ------------------------------------------------ */
 
 /* 1 if a layer with `k` inputs and `m` outputs is taken by the tcgen05 path (multiples of 64). */

@@ -69,6 +69,9 @@ SIGNATURES = {
     "mri_hashdecoder_backward": [_P, _I64, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, ctypes.POINTER(Level), _I, _I, _P, _P, _P,
                                  _P, _P],
     "mri_hashdecoder_forward": [_P, _I64, _I, _P, ctypes.POINTER(Level), _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "mri_hashmlp_mse_step_supported": [_I, _I, _I, _I, _I],
+    "mri_hashmlp_mse_step": [_P, _P, _I64, _I, _P, ctypes.POINTER(Level), _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _F, _P,
+                             ctypes.POINTER(Level), _P, _P, _P, _P, _P, _P, _P],
     "mri_siren_tc_supported": [_I, _I],
     "mri_siren_tc_split": [_P, _I64, _P, _P, _P],
     "mri_siren_tc_layer": [_P, _P, _P, _P, _P, _I64, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],

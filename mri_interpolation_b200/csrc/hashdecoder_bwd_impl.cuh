@@ -17,6 +17,11 @@ constexpr int BWD_THREADS = 32 * BWD_WARPS;
 
 constexpr int ACT_RUNTIME = -1;  // ACT1 template value: GELU / ReLU chosen by the kernel argument `act1`
 template <int ACT1>
+__device__ __forceinline__ float hidden_act_only(float pre, int act1) {
+  if constexpr (ACT1 >= 0) return activate<ACT1>(pre, 1.0f);
+  else return act1 == MRI_ACT_GELU ? activate<MRI_ACT_GELU>(pre, 1.0f) : activate<MRI_ACT_RELU>(pre, 1.0f);
+}
+template <int ACT1>
 __device__ __forceinline__ void hidden_act_and_grad(float pre, int act1, float& a, float& g) {
   if constexpr (ACT1 >= 0) {
     act_and_grad<ACT1>(pre, a, g);
@@ -48,7 +53,15 @@ constexpr size_t fused_bwd_smem_bytes() {
 //       odd) exchange their two levels with one shuffle and act as the lower / upper axis-0 halves of the pair-lane
 //       scatter (hash_device.cuh); on the coarse levels duplicates along an axis-0 line are merged first.
 // db1 / dw2 / db2 are per-thread column partials reduced once at the end.
-template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
+//
+// STEP = true turns the kernel into the WHOLE training step of HashMLP under the mean-squared-error loss
+// (models.py:61-66 + 741-744 and their autograd) in one pass over the batch: the tile's encoding is gathered here (the
+// forward kernel's gather, hashdecoder_fwd_impl.cuh) instead of being read back, the prediction and its loss gradient
+// 2 (y - target) / n are formed on the spot - the mean's gradient needs no global reduction first - and the backward
+// continues on the SAME accumulators: no (n, 32) encoding and no pre-activation ever go to memory, the hidden layer is
+// not recomputed, and the gather's L2 loads overlap the scatter's L2 reductions (two different units of the L2) instead
+// of running in two kernels back to back.
+template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS, bool STEP = false>
 __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_bwd_kernel(const float* __restrict__ enc, int64_t n,
                                                                            const float* __restrict__ w1, const float* __restrict__ b1,
                                                                            const float* __restrict__ w2, const float* __restrict__ pre2,
@@ -56,7 +69,14 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
                                                                            const float* __restrict__ x, const __grid_constant__ LevelTable T,
                                                                            float* __restrict__ grad_tables, float* __restrict__ gw1,
                                                                            float* __restrict__ gb1, float* __restrict__ gw2,
-                                                                           float* __restrict__ gb2) {
+                                                                           float* __restrict__ gb2,
+                                                                           // STEP only: tables to gather from, regression targets, output bias,
+                                                                           // 1 / n of the mean, loss accumulator, optional predictions
+                                                                           const float* __restrict__ tables = nullptr,
+                                                                           const float* __restrict__ target = nullptr,
+                                                                           const float* __restrict__ b2 = nullptr, float inv_count = 0.0f,
+                                                                           float* __restrict__ loss_out = nullptr,
+                                                                           float* __restrict__ y_out = nullptr) {
   static_assert((K0 == 8 || K0 == 16 || K0 == 32) && H % 16 == 0, "F = 2, L = 4 / 8 / 16");
   constexpr int KP = K0 < 16 ? 16 : K0;
   constexpr int WS = KP + MMA_PAD;   // row stride of W1 / enc planes (bf16 elements)
@@ -96,12 +116,15 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
 #pragma unroll
   for (int nt = 0; nt < H / 8; ++nt) { pb1[nt][0] = pb1[nt][1] = 0.0f; pw2[nt][0] = pw2[nt][1] = 0.0f; }
   float pb2 = 0.0f;
+  float ploss = 0.0f;
+  float b2v = 0.0f;
+  if constexpr (STEP) b2v = __ldg(b2);
 
   // inputs of one 16-row m-tile as they come out of global memory; the next tile's are requested before the current
   // tile is processed
   struct TileIn {
     float2 e[KP / 16][2][2];  // [k-tile][8-column half][row g / g+8]
-    float gy[2], p2[2];
+    float gy[2], p2[2];  // STEP: gy holds the regression targets
     float xv[2][D];
   };
   auto fetch = [&](int64_t row0, TileIn& ti) {
@@ -110,15 +133,19 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
     for (int rr = 0; rr < 2; ++rr) {
       const bool live = r[rr] < n;
       load_coord<D>(x, live ? r[rr] : 0, ti.xv[rr]);
-      ti.gy[rr] = live ? __ldg(gy + r[rr]) : 0.0f;
-      ti.p2[rr] = live ? __ldg(pre2 + r[rr]) : 0.0f;
+      if constexpr (STEP) {
+        ti.gy[rr] = live ? __ldg(target + r[rr]) : 0.0f;
+      } else {
+        ti.gy[rr] = live ? __ldg(gy + r[rr]) : 0.0f;
+        ti.p2[rr] = live ? __ldg(pre2 + r[rr]) : 0.0f;
 #pragma unroll
-      for (int kt = 0; kt < KP / 16; ++kt)
+        for (int kt = 0; kt < KP / 16; ++kt)
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
-          ti.e[kt][half][rr] = (live && 16 * kt + 8 * half < K0)  // columns K0 .. KP-1 are padding (L = 4)
-                                   ? __ldg(reinterpret_cast<const float2*>(enc + r[rr] * K0 + 16 * kt + 8 * half + 2 * t))
-                                   : make_float2(0.0f, 0.0f);
+          for (int half = 0; half < 2; ++half)
+            ti.e[kt][half][rr] = (live && 16 * kt + 8 * half < K0)  // columns K0 .. KP-1 are padding (L = 4)
+                                     ? __ldg(reinterpret_cast<const float2*>(enc + r[rr] * K0 + 16 * kt + 8 * half + 2 * t))
+                                     : make_float2(0.0f, 0.0f);
+      }
     }
   };
 
@@ -161,13 +188,41 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
     float acc[H / 8][4];
     {
       uint32_t a_hi[KP / 16][4], a_lo[KP / 16][4];
+      if constexpr (STEP) {
+        // the forward kernel's gather: lanes t, t^1 are the axis-0 pair, each walks its half of the corners of the pair's two
+        // levels for both rows; one shuffle completes the level sums and leaves level 4q + t of rows g / g+8 in this lane
+        if constexpr (K0 < KP) a_hi[0][2] = a_hi[0][3] = a_lo[0][2] = a_lo[0][3] = 0u;
+        const int b0g = t & 1;
 #pragma unroll
-      for (int kt = 0; kt < KP / 16; ++kt)
+        for (int q = 0; q < K0 / 8; ++q) {
+          Feat<2> part[2][2];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
-          split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+          for (int which = 0; which < 2; ++which) {
+            const LevelDev lv = lvs[4 * q + (t & 2) + which];
+            encode_half_level_rows<D>(make_cell<D>(xv_lo, lv), make_cell<D>(xv_hi, lv), b0g, lv, tables + lv.offset, part[which][0],
+                                      part[which][1]);
+          }
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            float full[2];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              const float mine = b0g ? part[1][rr].v[f] : part[0][rr].v[f];
+              const float send = b0g ? part[0][rr].v[f] : part[1][rr].v[f];
+              full[f] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+            }
+            split_pair(full[0], full[1], a_hi[q >> 1][2 * (q & 1) + rr], a_lo[q >> 1][2 * (q & 1) + rr]);
+          }
         }
+      } else {
+#pragma unroll
+        for (int kt = 0; kt < KP / 16; ++kt)
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            split_pair(cur.e[kt][half][0].x, cur.e[kt][half][0].y, a_hi[kt][2 * half + 0], a_lo[kt][2 * half + 0]);
+            split_pair(cur.e[kt][half][1].x, cur.e[kt][half][1].y, a_hi[kt][2 * half + 1], a_lo[kt][2 * half + 1]);
+          }
+      }
 #pragma unroll
       for (int kt = 0; kt < KP / 16; ++kt)
 #pragma unroll
@@ -181,8 +236,34 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
       hidden_mma<KP, H>(a_hi, a_lo, w_hi, w_lo, b1s, g, t, acc);
     }
     float dp2_lo = 0.0f, dp2_hi = 0.0f;
-    if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
-    if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
+    if constexpr (STEP) {
+      // prediction of rows g / g+8 (decoder layer 2 on the accumulator fragments, quad reduction), loss and its gradient
+      float s_lo = 0.0f, s_hi = 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < H / 8; ++nt) {
+        const float wl = w2s[8 * nt + 2 * t], wh = w2s[8 * nt + 2 * t + 1];
+        s_lo = fmaf(hidden_act_only<ACT1>(acc[nt][0], act1), wl, s_lo);
+        s_lo = fmaf(hidden_act_only<ACT1>(acc[nt][1], act1), wh, s_lo);
+        s_hi = fmaf(hidden_act_only<ACT1>(acc[nt][2], act1), wl, s_hi);
+        s_hi = fmaf(hidden_act_only<ACT1>(acc[nt][3], act1), wh, s_hi);
+      }
+      s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 1); s_lo += __shfl_xor_sync(0xffffffffu, s_lo, 2);
+      s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 1); s_hi += __shfl_xor_sync(0xffffffffu, s_hi, 2);
+      const float p_lo = s_lo + b2v, p_hi = s_hi + b2v;
+      const float y_lo = activate_rt(act2, p_lo, 1.0f), y_hi = activate_rt(act2, p_hi, 1.0f);
+      const float e_lo_ = y_lo - cur.gy[0], e_hi_ = y_hi - cur.gy[1];
+      if (r_lo < n) {
+        dp2_lo = 2.0f * e_lo_ * inv_count * activate_grad_rt(act2, p_lo, 1.0f);
+        if (t == 0) { ploss = fmaf(e_lo_, e_lo_, ploss); if (y_out) y_out[r_lo] = y_lo; }
+      }
+      if (r_hi < n) {
+        dp2_hi = 2.0f * e_hi_ * inv_count * activate_grad_rt(act2, p_hi, 1.0f);
+        if (t == 0) { ploss = fmaf(e_hi_, e_hi_, ploss); if (y_out) y_out[r_hi] = y_hi; }
+      }
+    } else {
+      if (r_lo < n) dp2_lo = cur.gy[0] * activate_grad_rt(act2, cur.p2[0], 1.0f);
+      if (r_hi < n) dp2_hi = cur.gy[1] * activate_grad_rt(act2, cur.p2[1], 1.0f);
+    }
     if (t == 0) pb2 += dp2_lo + dp2_hi;
     float dacc[K0 / 8][4];
     {
@@ -323,6 +404,11 @@ __global__ void __launch_bounds__(BWD_THREADS, H == 64 ? 2 : 1) hashdecoder_mma_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) pb2 += __shfl_xor_sync(0xffffffffu, pb2, o);
   if (lane == 0) red_add_f32(gb2, pb2);
+  if constexpr (STEP) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ploss += __shfl_xor_sync(0xffffffffu, ploss, o);
+    if (lane == 0) red_add_f32(loss_out, ploss * inv_count);
+  }
 }
 
 template <int D, int K0, int H, int ACT1, int MERGE_NT2, bool CONTIGUOUS>
@@ -344,8 +430,34 @@ int launch_fused_bwd(const float* enc, int64_t n, const float* w1, const float* 
   int64_t blocks = ((n + 15) / 16 + BWD_WARPS - 1) / BWD_WARPS;
   if (blocks > resident) blocks = resident;
   kernel<<<static_cast<int>(blocks), BWD_THREADS, smem, s>>>(enc, n, w1, b1, w2, pre2, gy, act1, act2, x, T, grad_tables, gw1, gb1,
-                                                             gw2, gb2);
+                                                             gw2, gb2, nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr);
   MRI_LAUNCH_OK("hashdecoder_mma_bwd_kernel");
+  return MRI_OK;
+}
+
+
+// the whole HashMLP + MSE training step (STEP = true): same launch shape as the backward
+template <int D, int K0, int H, int ACT1, int MERGE_NT2>
+int launch_fused_step(const float* x, const float* target, int64_t n, const float* tables, const LevelTable& T, const float* w1,
+                      const float* b1, const float* w2, const float* b2, int act1, int act2, float inv_count, float* grad_tables,
+                      float* gw1, float* gb1, float* gw2, float* gb2, float* loss_out, float* y_out, cudaStream_t s) {
+  constexpr size_t smem = fused_bwd_smem_bytes<K0, H>();
+  auto kernel = hashdecoder_mma_bwd_kernel<D, K0, H, ACT1, MERGE_NT2, true, true>;
+  static DeviceCache resident_cache;
+  const int dev = DeviceCache::device();
+  int resident = resident_cache.slot[dev].load(std::memory_order_acquire);
+  if (resident == 0) {
+    MRI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    MRI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BWD_THREADS, smem));
+    resident = (per_sm > 0 ? per_sm : 1) * sm_count();
+    resident_cache.slot[dev].store(resident, std::memory_order_release);
+  }
+  int64_t blocks = ((n + 15) / 16 + BWD_WARPS - 1) / BWD_WARPS;
+  if (blocks > resident) blocks = resident;
+  kernel<<<static_cast<int>(blocks), BWD_THREADS, smem, s>>>(nullptr, n, w1, b1, w2, nullptr, nullptr, act1, act2, x, T, grad_tables, gw1,
+                                                             gb1, gw2, gb2, tables, target, b2, inv_count, loss_out, y_out);
+  MRI_LAUNCH_OK("hashdecoder_mma_bwd_kernel<step>");
   return MRI_OK;
 }
 

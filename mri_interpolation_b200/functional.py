@@ -335,6 +335,51 @@ class HashDecoderFn(torch.autograd.Function):
         return (None, None, pret[0], pret[1], pret[2], pret[3], None, None) + tret
 
 
+def hashmlp_mse_step_supported(dim: int, n_levels: int, n_features: int, h: int, act1: int) -> bool:
+    return bool(_lib.lib().mri_hashmlp_mse_step_supported(int(dim), int(n_levels), int(n_features), int(h), int(act1)))
+
+
+def _grad_buffer(p: torch.Tensor) -> torch.Tensor:
+    """The buffer a backward kernel accumulates into: the parameter's .grad (normally a view of the optimiser's flat
+    gradient arena), created as zeros when the parameter has none yet."""
+    g = _direct_grad(p)
+    if g is None:
+        if not p.is_leaf:
+            raise MriB200Error("fused training step: parameters must be leaf tensors")
+        p.grad = torch.zeros_like(p)
+        g = _direct_grad(p)
+    return g
+
+
+@torch.no_grad()
+def hashmlp_mse_step(x: torch.Tensor, target: torch.Tensor, grid, w1, b1, w2, b2, act1: int, act2: int,
+                     want_pred: bool = False):
+    """loss = F.mse_loss(target, decoder(encoder(x))) AND its backward in ONE kernel (mri_hashmlp_mse_step): the gradients
+    of the tables and the decoder accumulate into the parameters' .grad buffers, nothing else is written.  Returns
+    (loss 0-dim tensor, predictions (n, 1) or None).  The mean's gradient 2 (y - t) / n needs no reduction over the batch
+    first, so forward, loss and backward of a tile run back to back on one set of registers."""
+    n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
+    x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
+    t2 = _lib.require_cuda_f32(target, "target").reshape(-1).contiguous()
+    n = x2.shape[0]
+    if t2.shape[0] != n:
+        raise MriB200Error(f"fused training step: {n} coordinates but {t2.shape[0]} targets (one output per coordinate)")
+    tables = grid.tables()
+    grid._fwd_layout.refresh(tables, grid._resolutions, grid._rows)
+    gtables = [_grad_buffer(t) for t in tables]
+    grid._bwd_layout.refresh(gtables, grid._resolutions, grid._rows)
+    gw1, gb1, gw2, gb2 = (_grad_buffer(p) for p in (w1, b1, w2, b2))
+    h, k0 = w1.shape
+    loss = torch.zeros((), device=x.device, dtype=torch.float32)
+    pred = torch.empty((n, 1), device=x.device, dtype=torch.float32) if want_pred else None
+    if n > 0:
+        _lib.call("mri_hashmlp_mse_step", x2.data_ptr(), t2.data_ptr(), n, dim, grid._fwd_layout.base, grid._fwd_layout.levels,
+                  n_levels, nf, k0, h, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), act1, act2, 1.0 / n,
+                  grid._bwd_layout.base, grid._bwd_layout.levels, gw1.data_ptr(), gb1.data_ptr(), gw2.data_ptr(), gb2.data_ptr(),
+                  loss.data_ptr(), _lib.ptr(pred), _lib.stream())
+    return loss, pred
+
+
 def hashdecoder_supported(dim: int, n_levels: int, n_features: int, h: int, act1: int) -> bool:
     return bool(_lib.lib().mri_hashdecoder_supported(int(dim), int(n_levels), int(n_features), int(h), int(act1)))
 

@@ -331,6 +331,10 @@ class HashMLP(BaseMLP):
         self.latents = []  # encoder outputs kept by predict_step for visualisation (:689,749)
         self.keep_latents = True
         self.fuse_backward = os.environ.get("MRI_FUSED_BACKWARD", "1") == "1"
+        # forward + loss + backward as ONE kernel (fused_training_step): opt-in.  Measured on B200 (G4, 2^19 coords): 1.335 ms
+        # against 0.23 + 0.43 ms for the forward and backward kernels - at the backward's 12 warps per SM the gather's L2
+        # latency is exposed instead of overlapping the scatter (profiles/README.md), so two kernels stay the default.
+        self.fuse_step = os.environ.get("MRI_FUSED_STEP", "0") == "1"
 
         if isinstance(self.base_resolution, int):
             self.encoder = encoding.MultiResHashGrid(
@@ -420,6 +424,31 @@ class HashMLP(BaseMLP):
             l1, l2, a1, a2 = plan
             return Fn.HashDecoderFn.apply(x, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2, *enc.tables())
         return self.decode(self.encoder(x))
+
+    def fused_training_step(self, batch, batch_idx):
+        """``training_step`` + ``loss.backward()`` in ONE kernel (csrc/hashdecoder_step.cu): returns the loss (a detached
+        0-dim tensor, logged as ``train_loss``) with the gradients already accumulated in the parameters' .grad buffers,
+        or None when this model / batch has no fused step (the caller then runs training_step + backward).  Opt-in
+        (``MRI_FUSED_STEP=1`` or ``model.fuse_step = True``; the Trainer stand-in then takes this path by itself);
+        models.py:61-66, 741-744."""
+        x, y = batch
+        plan = self._fused_decoder_plan() if (x.is_cuda and self.fuse_backward and self.fuse_step) else None
+        enc = self.encoder
+        if (plan is None or not torch.is_grad_enabled() or getattr(enc, "_resolutions", None) is None
+                or getattr(enc, "_grad_group_hook", None) is not None
+                or y.numel() != x.reshape(-1, x.shape[-1]).shape[0]
+                or not Fn.hashmlp_mse_step_supported(enc.dim, enc.n_levels, enc.n_features_per_level, plan[0].out_features, plan[2])):
+            return None
+        l1, l2, a1, a2 = plan
+        params = list(enc.tables()) + [l1.weight, l1.bias, l2.weight, l2.bias]
+        if not all(p.is_leaf and p.requires_grad for p in params):
+            return None
+        tabs = enc.tables()
+        if any(t.grad is None or t.grad.data_ptr() - tabs[0].grad.data_ptr() != t.data_ptr() - tabs[0].data_ptr() for t in tabs):
+            return None  # the kernel takes ONE level layout for the tables and their gradients (true for the flat arenas)
+        loss, _ = Fn.hashmlp_mse_step(x, y, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
+        self.log("train_loss", loss)
+        return loss
 
     def predict_step(self, batch, batch_idx):
         x, y = batch

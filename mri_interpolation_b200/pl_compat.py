@@ -170,6 +170,22 @@ def _move(batch, device):
     return batch
 
 
+def training_step_and_backward(model, batch, batch_idx):
+    """What Lightning's loop does between two optimiser steps: ``loss = model.training_step(batch)``, ``loss.backward()``.
+    A module that offers ``fused_training_step`` (HashMLP under the MSE loss: forward, loss and backward in ONE kernel)
+    is asked first; it returns None when it has no fused path for this batch.  Returns the (detached) loss."""
+    fused = getattr(model, "fused_training_step", None)
+    if fused is not None:
+        loss = fused(batch, batch_idx)
+        if loss is not None:
+            return loss
+    loss = model.training_step(batch, batch_idx)
+    if isinstance(loss, dict):
+        loss = loss["loss"]
+    loss.backward()
+    return loss.detach()
+
+
 class Trainer:
     def __init__(self, accelerator: str = "auto", devices: Any = "auto", max_epochs: Optional[int] = None,
                  accumulate_grad_batches: Any = None, precision: Any = 32, logger: Any = True,
@@ -298,10 +314,13 @@ class Trainer:
                             stop = True
                             break
                         continue
-                loss = model.training_step(batch, batch_idx)
-                if isinstance(loss, dict):
-                    loss = loss["loss"]
-                (loss / accum if accum > 1 else loss).backward()
+                if accum == 1:
+                    training_step_and_backward(model, batch, batch_idx)
+                else:
+                    loss = model.training_step(batch, batch_idx)
+                    if isinstance(loss, dict):
+                        loss = loss["loss"]
+                    (loss / accum).backward()
                 pending += 1
                 if pending == accum:
                     self.optimizer.step()

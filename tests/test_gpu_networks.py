@@ -627,3 +627,99 @@ def test_hashmlp_spectral_norm_legacy_recipe_tracks_torch(batch_norm):
         if v.dtype.is_floating_point and v.numel() > 1:
             # ... and those bias steps feed the running means, hence the wider bound with BatchNorm
             assert rel_err(sd[k], v) < (1e-2 if batch_norm else 2e-3), k
+
+
+@pytest.mark.parametrize("gi", [0, 1, 2, 3])
+@pytest.mark.parametrize("act", ["gelu", "relu"])
+def test_one_kernel_training_step_matches_training_step_plus_backward_and_oracle(gi, act):
+    """HashMLP.fused_training_step (mri_hashmlp_mse_step: gather + decoder + MSE + decoder backward + scatter in ONE
+    kernel) against training_step + loss.backward() (two kernels + MSE kernel) and the oracle: same loss, same gradients;
+    gradients accumulate over two calls like autograd's."""
+    import copy
+    from mri_interpolation_b200 import models
+    from mri_interpolation_b200.pl_compat import training_step_and_backward
+    from oracle import networks
+    geo = FUSED_GEOMETRIES[gi]
+    dim = geo["dim_in"]
+    kw = dict(n_levels=16, n_features_per_level=2, dim_hidden=64, dim_out=1, n_layers=2, **geo)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, activation=torch.nn.ReLU if act == "relu" else torch.nn.GELU)
+    oact = F.relu if act == "relu" else F.gelu
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.2)
+    params = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items() if not k.startswith("layers.")}
+    aniso = not isinstance(geo["base_resolution"], int)
+    levels = networks.hashgrid.geometry(dim, 16, geo["log2_hashmap_size"], geo["base_resolution"], geo["finest_resolution"])
+    for n in (1, 17, 4099):
+        x, y = torch.rand(n, dim, generator=gen), torch.rand(n, 1, generator=gen)
+        if act == "relu":  # unambiguous gates only (see the backward test above)
+            with torch.no_grad():
+                tabs = [params[f"encoder.levels.{i}.embedding.weight"] for i in range(16)]
+                pre1 = F.linear(networks.hashgrid.encode(x, tabs, levels, aniso), params["decoder.0.0.weight"], params["decoder.0.0.bias"])
+                pre2 = F.linear(F.relu(pre1), params["decoder.1.0.weight"], params["decoder.1.0.bias"])
+            keep = (pre1.abs().min(dim=1).values > 1e-4) & (pre2.abs().min(dim=1).values > 1e-4)
+            x, y = x[keep], y[keep]
+            n = x.shape[0]
+            if n == 0:
+                continue
+        for p in params.values():
+            p.grad = None
+        lref = F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, aniso, oact))
+        lref.backward()
+        one, two = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
+        one.fuse_step, two.fuse_step = True, False
+        batch = (x.to(DEV), y.to(DEV))
+        assert one.fused_training_step(batch, 0) is None  # separately allocated gradients: no common level layout
+        one.configure_optimizers()                        # ... the flat arenas give the tables and their gradients one layout
+        two.configure_optimizers()
+        l1 = one.fused_training_step(batch, 0)
+        assert l1 is not None and l1.grad_fn is None and two.fused_training_step(batch, 0) is None
+        l2 = training_step_and_backward(two, batch, 0)
+        assert abs(float(l1) - float(lref)) < 1e-5 * max(1.0, float(lref)) and abs(float(l1) - float(l2)) < 1e-6
+        for (name, p1), (_, p2) in zip(one.named_parameters(), two.named_parameters()):
+            if name.startswith("layers."):
+                continue
+            ref = params[name].grad
+            scale = float(ref.abs().max()) + 1e-12
+            assert float((p1.grad.cpu() - ref).abs().max()) < 2e-3 * scale, (n, name)
+            assert float((p1.grad - p2.grad).abs().max()) < 2e-3 * scale, (n, name)
+            if n >= 17:
+                assert rel_err(p1.grad, ref) < 1e-3, (n, name)
+        # a second call accumulates (autograd semantics): gradients double
+        g_before = {k: p.grad.clone() for k, p in one.named_parameters() if p.grad is not None and not k.startswith("layers.")}
+        one.fused_training_step(batch, 1)
+        for k, p in one.named_parameters():
+            if k in g_before:
+                assert rel_err(p.grad, 2 * g_before[k]) < 1e-5, k
+
+
+def test_trainer_takes_the_one_kernel_step_and_matches_the_autograd_loop(tmp_path):
+    """Trainer.fit with the one-kernel step (default) and with MRI_FUSED_STEP switched off train to the same parameters."""
+    import copy
+    from mri_interpolation_b200 import _lib, models
+    from mri_interpolation_b200.datamodules import DeviceBatchLoader
+    from mri_interpolation_b200.pl_compat import pl
+    kw = dict(dim_in=4, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=200,
+              dim_hidden=64, dim_out=1, n_layers=2)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, lr=5e-3)
+    gen = torch.Generator().manual_seed(3)
+    coords, pix = torch.rand(5000, 4, generator=gen), torch.rand(5000, 1, generator=gen)
+    results = []
+    for fuse in (True, False):
+        m = copy.deepcopy(net)
+        m.fuse_step = fuse  # opt-in (default off: measured slower than the two-kernel step)
+        loader = DeviceBatchLoader(coords, pix, 1024, shuffle=True, device=DEV, seed=11)
+        tr = pl.Trainer(accelerator="gpu", max_epochs=2, precision=32, default_root_dir=str(tmp_path), enable_checkpointing=False,
+                        cuda_graph=False)
+        before = _lib.launch_count
+        tr.fit(m, loader)
+        results.append((m, _lib.launch_count - before, float(tr.callback_metrics["train_loss"])))
+    (a, la, lossa), (b, lb, lossb) = results
+    assert la < lb  # fewer launches: one kernel instead of forward + MSE + backward
+    assert abs(lossa - lossb) < 1e-5
+    for (k, p), (_, q) in zip(a.state_dict().items(), b.state_dict().items()):
+        if p.dtype.is_floating_point and p.numel() and float(q.norm()) > 0:
+            assert rel_err(p, q) < 1e-4, k
