@@ -15,10 +15,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libmri_b200.so")
-SOURCES = ["core.cu", "hashgrid.cu", "dense.cu", "optim.cu", "sweep.cu", "siren_tc.cu", "decoder.cu", "siren_edge.cu", "hashdecoder_fwd.cu",
+SOURCES = ["core.cu", "hashgrid.cu", "dense.cu", "optim.cu", "sweep.cu", "siren_tc.cu", "decoder.cu", "decoder_k16.cu", "decoder_k32.cu", "decoder_k64.cu", "siren_edge.cu", "hashdecoder_fwd.cu",
            "hashdecoder_bwd.cu", "metrics.cu", "probe.cu", "hashdecoder_fwd_geo.cu", "hashdecoder_bwd_geo.cu", "hashdecoder_step.cu"]
 HEADERS = ["common.cuh", "hash_device.cuh", "mma_device.cuh", "grid_device.cuh", "hashdecoder.cuh", "hashdecoder_fwd_impl.cuh",
-           "hashdecoder_bwd_impl.cuh", "../../include/mri_b200.h"]
+           "hashdecoder_bwd_impl.cuh", "decoder_impl.cuh", "../../include/mri_b200.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
