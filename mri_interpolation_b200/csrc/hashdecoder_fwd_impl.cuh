@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(DEC_THREADS, H == 64 ? 5 : 3) hashdecoder_mma_
     src.load_pair(row0, n, lane, xv[0], xv[1]);
     uint32_t a_hi[KP / 16][4], a_lo[KP / 16][4];
     if constexpr (K0 < KP) a_hi[0][2] = a_hi[0][3] = a_lo[0][2] = a_lo[0][3] = 0u;  // L = 4: columns 8-15 of the k-tile are padding
-#pragma unroll
+    // A REAL loop over the 8-column halves (levels 4q .. 4q+3): unrolled, the gather of the four halves was 80-86 KB of SASS
+    // per kernel (33-38 KB now); the fragment registers are picked with a compile-time if-chain below.  Measured neutral
+    // on the B200 (0.228 vs 0.230 ms, sweep 3.1 vs 3.2 G voxels/s): ncu's stall_no_instruction (0.45-1.4 per issue) was not
+    // what held the kernel back - kept for the smaller binary.
+#pragma unroll 1
     for (int q = 0; q < K0 / 8; ++q) {  // q-th 8-column half: levels 4q .. 4q+3, this lane ends up with level 4q + t
       Feat<2> part[2][2];               // [level of the pair: even / odd][row g / g+8], this lane's axis-0 half
 #pragma unroll
@@ -152,7 +156,11 @@ __global__ void __launch_bounds__(DEC_THREADS, H == 64 ? 5 : 3) hashdecoder_mma_
           const float send = b0 ? part[0][rr].v[f] : part[1][rr].v[f];
           full[f] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
         }
-        split_pair(full[0], full[1], a_hi[q >> 1][2 * (q & 1) + rr], a_lo[q >> 1][2 * (q & 1) + rr]);
+        uint32_t hi_bits, lo_bits;
+        split_pair(full[0], full[1], hi_bits, lo_bits);
+#pragma unroll
+        for (int qq = 0; qq < K0 / 8; ++qq)  // static register indices: predicated moves, no local memory
+          if (qq == q) { a_hi[qq >> 1][2 * (qq & 1) + rr] = hi_bits; a_lo[qq >> 1][2 * (qq & 1) + rr] = lo_bits; }
         if (enc_out != nullptr && rows[rr] < n)
           *reinterpret_cast<float2*>(enc_out + rows[rr] * K0 + 2 * (4 * q + t)) = make_float2(full[0], full[1]);
       }
