@@ -61,11 +61,14 @@ class _Logger:
         return path
 
     def log_metrics(self, metrics: Dict[str, float], step: int) -> None:
-        self._rows.append({"step": step, **metrics})
+        # device scalars are kept as (cloned) tensors and read back in finalize(): a float() here would drain the GPU's
+        # launch queue every 50 steps and at every epoch end
+        self._rows.append({"step": step, **{k: (v.detach().clone() if isinstance(v, torch.Tensor) else v) for k, v in metrics.items()}})
 
     def finalize(self) -> None:
         if not self._rows:
             return
+        self._rows = [{k: (float(v) if isinstance(v, torch.Tensor) else v) for k, v in r.items()} for r in self._rows]
         keys: List[str] = []
         for r in self._rows:
             for k in r:
@@ -236,7 +239,7 @@ class Trainer:
         if self.logger is None or not self._pending:
             self._pending = {}
             return
-        row = {k: (float(v) if isinstance(v, torch.Tensor) else v) for k, v in self._pending.items()}
+        row = dict(self._pending)  # tensors stay on the device until the logger is finalised (no sync in the loop)
         self.logger.log_metrics(row, self.global_step)
         self._pending = {}
 
