@@ -142,6 +142,9 @@ int make_level_table(const mri_level_t* host_levels, int n_levels, int dim, Leve
   for (int l = 0; l < n_levels; ++l) {
     const mri_level_t& h = host_levels[l];
     if (h.rows == 0) return fail(MRI_ERR_INVALID, "hashgrid: level %d has 0 rows", l);
+    // exact_mod's estimate leaves a remainder below 2 * rows, which must fit 32 bits for non-power-of-two tables
+    if ((h.rows & (h.rows - 1)) != 0 && h.rows > 0x80000000u)
+      return fail(MRI_ERR_UNSUPPORTED, "hashgrid: level %d has %u rows; non-power-of-two tables are limited to 2^31 rows", l, h.rows);
     LevelDev& d = out->lv[l];
     for (int a = 0; a < MRI_MAX_DIM; ++a) d.res[a] = a < dim ? h.resolution[a] : 0.0f;
     d.rows = h.rows;

@@ -187,3 +187,26 @@ def test_cpu_input_is_rejected():
     enc = build_encoder(fx, DEV)
     with pytest.raises(MriB200Error):
         enc(torch.from_numpy(fx["x"]))
+
+
+@pytest.mark.parametrize("dim,base,finest,log2", [(2, 3, 1500, 22), (3, 5, 150, 24), (4, 3, 40, 24)])
+def test_multiply_based_modulo_is_exact_on_non_power_of_two_tables(dim, base, finest, log2):
+    """The coarse levels here have res^D < T rows, not powers of two (9 ... 3 307 949): the kernels reduce the 32-bit hash with exact_mod
+    (mulhi by floor(2^32 / rows) + one conditional subtraction) instead of a division - rows addressed by the shipped gather
+    kernel and the probe must equal the oracle's `%` bit for bit, for hashes over the whole 32-bit range."""
+    from mri_interpolation_b200 import encoding
+    from oracle import hashgrid
+    enc = encoding.MultiResHashGrid(dim, n_levels=6, n_features_per_level=2, log2_hashmap_size=log2, base_resolution=base,
+                                    finest_resolution=finest).to(DEV)
+    levels = hashgrid.geometry_isotropic(dim, 6, log2, base, finest)
+    assert sum(1 for lv in levels if lv.rows & (lv.rows - 1)) >= 3
+    gen = torch.Generator().manual_seed(dim)
+    x = torch.rand(20000, dim, generator=gen)
+    x[:64] = 1.0
+    x[64:128] = 0.0
+    _, rows = enc.gathered_rows(x.to(DEV))
+    h, _ = enc.corner_hashes(x.to(DEV))
+    for li, lv in enumerate(levels):
+        ho, _ = hashgrid.corners(x, lv)
+        assert torch.equal(rows[:, li].cpu(), ho), f"level {li} ({lv.rows} rows)"
+        assert torch.equal(h[:, li].cpu(), ho), f"level {li} ({lv.rows} rows): probe"
