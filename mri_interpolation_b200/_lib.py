@@ -149,7 +149,14 @@ def call(name: str, *args, kernels: int = 1) -> None:
     check(getattr(lib(), name)(*args), name)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream() -> int:
+    """cudaStream_t of torch's current stream on the current device.  The raw accessor skips the Stream object that
+    torch.cuda.current_stream() builds (25 us per call in the Trainer loop's profile, four calls per training step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
