@@ -113,7 +113,12 @@ class DeviceBatchLoader:
 
     def __init__(self, coords: torch.Tensor, pixels: torch.Tensor, batch_size: int, shuffle: bool = False,
                  device: Optional[torch.device] = None, seed: int = 1337, rank: int = 0, world_size: int = 1,
-                 drop_last: bool = False, grid_shape: Optional[Sequence[int]] = None, locality: bool = True):
+                 drop_last: bool = False, grid_shape: Optional[Sequence[int]] = None, locality: bool = True,
+                 grid_norm_siren: Optional[bool] = None):
+        """``grid_norm_siren`` (not None) declares that ``coords`` IS the dense ``mgrid_axes(grid_shape, grid_norm_siren)``
+        mesh in C order (what MriImage builds): shuffled CUDA batches are then produced by ``mri_gather_voxels`` - the
+        coordinates rebuilt from the voxel index, bit-identical - in 0.015 ms instead of the 0.27 ms
+        ``coords.index_select`` takes on the 11 M x 4 sample array (scripts/loader_cost.py)."""
         self.device = torch.device(device) if device is not None else coords.device
         self.coords = coords.to(self.device)
         self.pixels = pixels.to(self.device)
@@ -125,6 +130,12 @@ class DeviceBatchLoader:
         self.epoch = 0
         self.epochs = ShuffledEpochs(self.coords.shape[0], self.batch_size, self.device, seed, rank, world_size,
                                      grid_shape if shuffle else None, locality)
+        self._voxels = None
+        if (shuffle and grid_shape is not None and grid_norm_siren is not None and self.device.type == "cuda"
+                and self.pixels.dtype == torch.float32 and self.pixels.numel() == self.coords.shape[0]
+                and self.coords.shape[1] == len(grid_shape) and int(np.prod(grid_shape)) == self.coords.shape[0]):
+            from .functional import VoxelSampler
+            self._voxels = VoxelSampler(self.pixels.reshape(-1), grid_shape, norm_siren=bool(grid_norm_siren))
 
     def _draw_epoch(self) -> torch.Tensor:
         # drawn on the training stream: prefetching the next epoch on a side stream was measured SLOWER (Trainer.fit 371 vs
@@ -144,7 +155,10 @@ class DeviceBatchLoader:
             order = self._draw_epoch()
             for i in range(len(self)):
                 idx = order[i * self.batch_size:(i + 1) * self.batch_size]
-                yield self.coords.index_select(0, idx), self.pixels.index_select(0, idx)
+                if self._voxels is not None:
+                    yield self._voxels.batch(idx)
+                else:
+                    yield self.coords.index_select(0, idx), self.pixels.index_select(0, idx)
         else:
             if self.world_size > 1:
                 raise RuntimeError("unshuffled loaders are not sharded; use sweep.dense_sweep for inference")
@@ -226,6 +240,7 @@ class MriImage(Dataset):
         coords = mgrid.reshape(len(pixels), config.dim_in)
         assert len(coords) == len(pixels)
         self.shape = tuple(image.shape)
+        self.norm_siren = bool(norm_siren)
         self.coords = coords.contiguous()
         self.pixels = pixels.unsqueeze(-1)
 
@@ -266,7 +281,8 @@ class MriDataModule(pl.LightningDataModule):
         if shuffle and torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         return DeviceBatchLoader(ds.coords, ds.pixels, self.config.batch_size, shuffle=shuffle, device=self._dev(),
-                                 rank=rank, world_size=world, grid_shape=getattr(ds, "shape", None))
+                                 rank=rank, world_size=world, grid_shape=getattr(ds, "shape", None),
+                                 grid_norm_siren=getattr(ds, "norm_siren", None))
 
     def train_dataloader(self):
         return self._loader(self.train_ds, True)

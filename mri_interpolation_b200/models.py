@@ -335,6 +335,8 @@ class HashMLP(BaseMLP):
         # against 0.23 + 0.43 ms for the forward and backward kernels - at the backward's 12 warps per SM the gather's L2
         # latency is exposed instead of overlapping the scatter (profiles/README.md), so two kernels stay the default.
         self.fuse_step = os.environ.get("MRI_FUSED_STEP", "0") == "1"
+        # training_step + backward as three direct kernel calls (no autograd engine): default on
+        self.direct_step = os.environ.get("MRI_DIRECT_STEP", "1") == "1"
 
         if isinstance(self.base_resolution, int):
             self.encoder = encoding.MultiResHashGrid(
@@ -426,27 +428,38 @@ class HashMLP(BaseMLP):
         return self.decode(self.encoder(x))
 
     def fused_training_step(self, batch, batch_idx):
-        """``training_step`` + ``loss.backward()`` in ONE kernel (csrc/hashdecoder_step.cu): returns the loss (a detached
-        0-dim tensor, logged as ``train_loss``) with the gradients already accumulated in the parameters' .grad buffers,
-        or None when this model / batch has no fused step (the caller then runs training_step + backward).  Opt-in
-        (``MRI_FUSED_STEP=1`` or ``model.fuse_step = True``; the Trainer stand-in then takes this path by itself);
-        models.py:61-66, 741-744."""
+        """``training_step`` + ``loss.backward()`` without the autograd engine: returns the loss (a detached 0-dim tensor,
+        logged as ``train_loss``) with the gradients already accumulated in the parameters' .grad buffers, or None when
+        this model / batch has no such path (the caller then runs training_step + backward).  Two variants:
+        * direct (default, ``MRI_DIRECT_STEP=0`` switches it off): the SAME three kernels autograd would launch - fused
+          forward, MSE, fused backward - called back to back; bit-identical results, a quarter of the Python time;
+        * one kernel for all of it (csrc/hashdecoder_step.cu; opt-in with ``MRI_FUSED_STEP=1`` / ``fuse_step = True``,
+          headline geometry, measured slower on the GPU).
+        The Trainer stand-in asks for this path by itself (pl_compat.training_step_and_backward); models.py:61-66, 741-744."""
         x, y = batch
-        plan = self._fused_decoder_plan() if (x.is_cuda and self.fuse_backward and self.fuse_step) else None
+        plan = self._fused_decoder_plan() if (x.is_cuda and self.fuse_backward and (self.fuse_step or self.direct_step)) else None
         enc = self.encoder
         if (plan is None or not torch.is_grad_enabled() or getattr(enc, "_resolutions", None) is None
-                or getattr(enc, "_grad_group_hook", None) is not None
-                or y.numel() != x.reshape(-1, x.shape[-1]).shape[0]
-                or not Fn.hashmlp_mse_step_supported(enc.dim, enc.n_levels, enc.n_features_per_level, plan[0].out_features, plan[2])):
+                or getattr(enc, "_grad_group_hook", None) is not None or self.criterion is not Fn.mse_loss
+                or y.numel() != x.reshape(-1, x.shape[-1]).shape[0] or x.requires_grad
+                or not Fn.hashdecoder_supported(enc.dim, enc.n_levels, enc.n_features_per_level, plan[0].out_features, plan[2])):
             return None
         l1, l2, a1, a2 = plan
-        params = list(enc.tables()) + [l1.weight, l1.bias, l2.weight, l2.bias]
+        tabs = enc.tables()
+        params = list(tabs) + [l1.weight, l1.bias, l2.weight, l2.bias]
         if not all(p.is_leaf and p.requires_grad for p in params):
             return None
-        tabs = enc.tables()
-        if any(t.grad is None or t.grad.data_ptr() - tabs[0].grad.data_ptr() != t.data_ptr() - tabs[0].data_ptr() for t in tabs):
-            return None  # the kernel takes ONE level layout for the tables and their gradients (true for the flat arenas)
-        loss, _ = Fn.hashmlp_mse_step(x, y, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
+        one_kernel = (self.fuse_step
+                      and Fn.hashmlp_mse_step_supported(enc.dim, enc.n_levels, enc.n_features_per_level, plan[0].out_features, plan[2])
+                      # the one-kernel step takes ONE level layout for the tables and their gradients (true for the flat arenas)
+                      and not any(t.grad is None or t.grad.data_ptr() - tabs[0].grad.data_ptr() != t.data_ptr() - tabs[0].data_ptr()
+                                  for t in tabs))
+        if one_kernel:
+            loss, _ = Fn.hashmlp_mse_step(x, y, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
+        elif self.direct_step:
+            loss = Fn.hashmlp_mse_direct_step(x, y, enc, l1.weight, l1.bias, l2.weight, l2.bias, a1, a2)
+        else:
+            return None
         self.log("train_loss", loss)
         return loss
 

@@ -1,25 +1,28 @@
-"""What one shuffled epoch of indices costs on the device, plain vs locality-ordered (DeviceBatchLoader.epoch_indices)."""
-import os, sys, time
+"""Device time of what DeviceBatchLoader does per batch on the sample volume (CUDA events): epoch draw, index_select of the
+(11.15 M, 4) coordinate array and of the intensities, against mri_gather_voxels (coordinates synthesised from the index)."""
+import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mri_interpolation_b200 import datamodules
+import bench
+from mri_interpolation_b200 import config as cfgmod, datamodules
+from mri_interpolation_b200 import functional as Fn
 
-shape = (352, 352, 6, 15)
-n = int(np.prod(shape))
 dev = torch.device("cuda", 0)
-coords = torch.zeros(n, 1, device=dev)
-for bs in (10_000, 1 << 19):
-    for grid in (None, shape):
-        ld = datamodules.DeviceBatchLoader(coords, coords, bs, shuffle=True, device=dev, grid_shape=grid)
-        ld.epoch_indices(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(5):
-            ld.epoch_indices()
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) / 5 * 1e3
-        print(f"batch {bs:7d} locality={grid is not None}: {ms:.2f} ms per epoch of {len(ld)} batches = {ms / len(ld) * 1e3:.1f} us per batch")
-t0 = time.perf_counter()
-for _ in range(5):
-    torch.randperm(n, device=dev)
-torch.cuda.synchronize()
-print(f"torch.randperm({n}) alone: {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms")
+cfg = cfgmod.HashConfig(); cfg.image_path, cfg.batch_size = bench.SAMPLE, 1 << 19
+dm = datamodules.MriDataModule(config=cfg, device=dev); dm.prepare_data()
+loader = dm.train_dataloader()
+def timed(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+order = loader.epochs.epoch()
+idx = order[: 1 << 19]
+print("epoch draw ms", timed(lambda: loader.epochs.epoch(), 5), "per batch", timed(lambda: loader.epochs.epoch(), 5) / 21)
+print("coords.index_select ms", timed(lambda: loader.coords.index_select(0, idx)))
+print("pixels.index_select ms", timed(lambda: loader.pixels.index_select(0, idx)))
+sampler = Fn.VoxelSampler(loader.pixels.reshape(-1), dm.dataset.shape)
+print("mri_gather_voxels ms", timed(lambda: sampler.batch(idx)))

@@ -668,15 +668,23 @@ def test_one_kernel_training_step_matches_training_step_plus_backward_and_oracle
             p.grad = None
         lref = F.mse_loss(y, networks.hashmlp_forward(x, params, levels, 2, aniso, oact))
         lref.backward()
-        one, two = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
-        one.fuse_step, two.fuse_step = True, False
+        one, two, three = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
+        one.fuse_step, one.direct_step = True, False      # one kernel
+        two.fuse_step, two.direct_step = False, False     # autograd: forward kernel, MSE kernel, backward kernel
+        three.fuse_step, three.direct_step = False, True  # the same three kernels called directly (the default)
         batch = (x.to(DEV), y.to(DEV))
         assert one.fused_training_step(batch, 0) is None  # separately allocated gradients: no common level layout
-        one.configure_optimizers()                        # ... the flat arenas give the tables and their gradients one layout
-        two.configure_optimizers()
+        for m in (one, two, three):
+            m.configure_optimizers()                      # ... the flat arenas give the tables and their gradients one layout
         l1 = one.fused_training_step(batch, 0)
         assert l1 is not None and l1.grad_fn is None and two.fused_training_step(batch, 0) is None
         l2 = training_step_and_backward(two, batch, 0)
+        l3 = three.fused_training_step(batch, 0)
+        assert l3 is not None and l3.grad_fn is None and abs(float(l3) - float(l2)) <= 1e-6 * abs(float(l2))  # atomic partial sums
+        for (name, p3), (_, p2) in zip(three.named_parameters(), two.named_parameters()):
+            if not name.startswith("layers."):
+                # same kernels on the same inputs: equal up to the order in which the reductions land
+                assert rel_err(p3.grad, p2.grad) < 1e-6, name
         assert abs(float(l1) - float(lref)) < 1e-5 * max(1.0, float(lref)) and abs(float(l1) - float(l2)) < 1e-6
         for (name, p1), (_, p2) in zip(one.named_parameters(), two.named_parameters()):
             if name.startswith("layers."):
@@ -710,7 +718,7 @@ def test_trainer_takes_the_one_kernel_step_and_matches_the_autograd_loop(tmp_pat
     results = []
     for fuse in (True, False):
         m = copy.deepcopy(net)
-        m.fuse_step = fuse  # opt-in (default off: measured slower than the two-kernel step)
+        m.fuse_step = fuse  # opt-in (default off: measured slower than the two-kernel step); fuse False -> the direct step
         loader = DeviceBatchLoader(coords, pix, 1024, shuffle=True, device=DEV, seed=11)
         tr = pl.Trainer(accelerator="gpu", max_epochs=2, precision=32, default_root_dir=str(tmp_path), enable_checkpointing=False,
                         cuda_graph=False)
@@ -723,3 +731,33 @@ def test_trainer_takes_the_one_kernel_step_and_matches_the_autograd_loop(tmp_pat
     for (k, p), (_, q) in zip(a.state_dict().items(), b.state_dict().items()):
         if p.dtype.is_floating_point and p.numel() and float(q.norm()) > 0:
             assert rel_err(p, q) < 1e-4, k
+
+
+@pytest.mark.parametrize("n_levels,hidden", [(16, 64), (8, 64), (16, 128)])
+def test_direct_step_equals_the_autograd_loop_over_several_optimiser_steps(n_levels, hidden):
+    """pl_compat.training_step_and_backward with the direct step (default) and with it switched off (autograd: the same
+    kernels behind two Functions) train to the same parameters; x.requires_grad or a custom criterion fall back."""
+    import copy
+    from mri_interpolation_b200 import models
+    from mri_interpolation_b200.pl_compat import training_step_and_backward
+    kw = dict(dim_in=4, n_levels=n_levels, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16, finest_resolution=200,
+              dim_hidden=hidden, dim_out=1, n_layers=2)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, lr=5e-3)
+    gen = torch.Generator().manual_seed(9)
+    direct, auto = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
+    auto.direct_step = False
+    od, oa = direct.configure_optimizers(), auto.configure_optimizers()
+    for step in range(4):
+        x, y = torch.rand(3000, 4, generator=gen).to(DEV), torch.rand(3000, 1, generator=gen).to(DEV)
+        ld = training_step_and_backward(direct, (x, y), step)
+        la = training_step_and_backward(auto, (x, y), step)
+        assert abs(float(ld) - float(la)) <= 1e-5 * abs(float(la))
+        od.step(); od.zero_grad(); oa.step(); oa.zero_grad()
+    for (k, p), (_, q) in zip(direct.state_dict().items(), auto.state_dict().items()):
+        if p.dtype.is_floating_point and p.numel() and float(q.norm()) > 0:
+            assert rel_err(p, q) < 1e-5, k
+    x = torch.rand(100, 4, generator=gen).to(DEV).requires_grad_()
+    assert direct.fused_training_step((x, torch.rand(100, 1, device=DEV)), 0) is None
+    direct.criterion = torch.nn.functional.l1_loss
+    assert direct.fused_training_step((x.detach(), torch.rand(100, 1, device=DEV)), 0) is None

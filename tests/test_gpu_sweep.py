@@ -351,3 +351,27 @@ def test_gpu_metrics_on_the_sample_volume_and_linear_time_baseline(tmp_path):
     text = open(tmp_path / "scores.txt").read()
     assert "MSE : " in text and "PSNR : " in text and "SSIM : " in text and "Number of trainable parameters : 7" in text
     assert scores["PSNR"] == pytest.approx(osweep.psnr(data, want), abs=1e-9)
+
+
+def test_mri_datamodule_batches_from_the_gather_kernel_equal_index_select(tmp_path):
+    """MriDataModule's shuffled CUDA loader rebuilds the coordinates from the voxel index (mri_gather_voxels) instead of
+    index_select on the materialised mesh: every batch is bit-identical to coords[idx], pixels[idx] of the same epoch."""
+    from mri_interpolation_b200 import config as cfgmod, datamodules, nifti
+    rng = np.random.default_rng(3)
+    vol = rng.random((11, 7, 3, 5)).astype(np.float32)
+    path = str(tmp_path / "vol.nii.gz")
+    nifti.save(vol, path)
+    cfg = cfgmod.HashConfig()
+    cfg.image_path, cfg.batch_size, cfg.dim_in = path, 300, 4
+    dm = datamodules.MriDataModule(config=cfg, device=DEV)
+    dm.prepare_data()
+    fast = dm.train_dataloader()
+    assert fast._voxels is not None
+    slow = datamodules.DeviceBatchLoader(dm.dataset.coords, dm.dataset.pixels, 300, shuffle=True, device=DEV,
+                                         grid_shape=dm.dataset.shape)  # same seed, no grid declaration: index_select
+    assert slow._voxels is None
+    n = 0
+    for (xa, ya), (xb, yb) in zip(fast, slow):
+        assert torch.equal(xa, xb) and torch.equal(ya, yb)
+        n += xa.shape[0]
+    assert n == vol.size
