@@ -2,6 +2,7 @@
 // hashdecoder_fwd.cu (headline geometry F = 2, L = 16, H = 64 with compile-time activation, plus the dense-sweep
 // coordinate sources) and hashdecoder_fwd_geo.cu (the other F = 2 geometries: L = 4 / 8 / 16, H = 64 / 128).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 #include "grid_device.cuh"
 #include "hash_device.cuh"
@@ -13,6 +14,10 @@ namespace {
 // coordinates of rows (row0 + g, row0 + g + 8) of a tile, from a (n, D) batch ...
 template <int D>
 struct BatchCoords {
+  // tile walk: a warp's consecutive tiles are a grid stride apart.  Measured on the B200 (2^19 locality-ordered
+  // coordinates): 0.230 ms against 0.258 ms with a contiguous range per warp - the random-subset batch has little to
+  // reuse from one tile to the next and the contiguous walk ends with a ragged tail
+  static constexpr bool kContiguousTiles = false;
   const float* x;
   __device__ __forceinline__ void load_pair(int64_t row0, int64_t n, int lane, float (&lo)[D], float (&hi)[D]) const {
     const int64_t r_lo = row0 + (lane >> 2), r_hi = r_lo + 8;
@@ -25,6 +30,7 @@ struct BatchCoords {
 // their two rows up with shuffles (no 4x redundant integer divisions)
 template <int D>
 struct SweepCoords {
+  static constexpr bool kContiguousTiles = true;
   const float* axes;
   GridDesc gd;
   int64_t first;
@@ -48,6 +54,9 @@ struct SweepCoords {
 // voxel's C-order position, so the output volume is the same array.
 template <int D>
 struct SweepCoordsAxis0 {
+  // dense walk: every warp takes its own contiguous range of tiles, so the coarse-level rows gathered for one tile are
+  // still in the SM's L1 for the next (measured: 6.59 vs 7.07 ms for the 21.6 M-voxel sweep)
+  static constexpr bool kContiguousTiles = true;
   const float* axes;
   GridDesc gd;
   int64_t out_base;   // C-order index of the box's first voxel minus the C-order index out[0] stands for
@@ -124,8 +133,13 @@ __global__ void __launch_bounds__(DEC_THREADS, H == 64 ? 5 : 3) hashdecoder_mma_
   const int g = lane >> 2, t = lane & 3;
   const int b0 = t & 1;  // axis-0 half of the pair-lane mapping
   const int64_t tiles = (n + 15) / 16;
-  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * (DEC_THREADS / 32) + warp; tile < tiles;
-       tile += static_cast<int64_t>(gridDim.x) * (DEC_THREADS / 32)) {
+  constexpr bool contiguous_tiles = Coords::kContiguousTiles;  // see the coordinate sources above
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (DEC_THREADS / 32);
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * (DEC_THREADS / 32) + warp;
+  const int64_t tile_begin = contiguous_tiles ? (wid * tiles) / n_warps : wid;
+  const int64_t tile_end = contiguous_tiles ? ((wid + 1) * tiles) / n_warps : tiles;
+  const int64_t tile_step = contiguous_tiles ? 1 : n_warps;
+  for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
     const int64_t row0 = tile * 16;
     const int64_t rows[2] = {row0 + g, row0 + g + 8};
     float xv[2][D];
