@@ -55,7 +55,7 @@ struct SweepCoords {
 template <int D>
 struct SweepCoordsAxis0 {
   // dense walk: every warp takes its own contiguous range of tiles, so the coarse-level rows gathered for one tile are
-  // still in the SM's L1 for the next (measured: 6.59 vs 7.07 ms for the 21.6 M-voxel sweep)
+  // still in the SM's L1 for the next (measured: 6.50 vs 7.07 ms for the 21.6 M-voxel sweep; see the kernel's tile loop)
   static constexpr bool kContiguousTiles = true;
   const float* axes;
   GridDesc gd;
@@ -134,11 +134,17 @@ __global__ void __launch_bounds__(DEC_THREADS, H == 64 ? 5 : 3) hashdecoder_mma_
   const int b0 = t & 1;  // axis-0 half of the pair-lane mapping
   const int64_t tiles = (n + 15) / 16;
   constexpr bool contiguous_tiles = Coords::kContiguousTiles;  // see the coordinate sources above
-  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (DEC_THREADS / 32);
-  const int64_t wid = static_cast<int64_t>(blockIdx.x) * (DEC_THREADS / 32) + warp;
-  const int64_t tile_begin = contiguous_tiles ? (wid * tiles) / n_warps : wid;
-  const int64_t tile_end = contiguous_tiles ? ((wid + 1) * tiles) / n_warps : tiles;
-  const int64_t tile_step = contiguous_tiles ? 1 : n_warps;
+  constexpr int WARPS = DEC_THREADS / 32;
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * WARPS;
+  const int64_t wid = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+  // contiguous: the BLOCK owns a contiguous range of tiles and its four warps interleave inside it - neighbouring tiles at
+  // the same time (shared L1 lines now) and in sequence (still in L1 next).  Sweep of 21.6 M voxels: grid stride 7.07 ms,
+  // one range per warp 6.62 ms, one range per block 6.50 ms.
+  const int64_t blk_begin = (static_cast<int64_t>(blockIdx.x) * tiles) / gridDim.x;
+  const int64_t blk_end = ((static_cast<int64_t>(blockIdx.x) + 1) * tiles) / gridDim.x;
+  const int64_t tile_begin = contiguous_tiles ? blk_begin + warp : wid;
+  const int64_t tile_end = contiguous_tiles ? blk_end : tiles;
+  const int64_t tile_step = contiguous_tiles ? WARPS : n_warps;
   for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
     const int64_t row0 = tile * 16;
     const int64_t rows[2] = {row0 + g, row0 + g + 8};
