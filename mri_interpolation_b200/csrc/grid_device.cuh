@@ -52,9 +52,11 @@ inline int make_grid_desc(const int32_t* host_shape, int dim, GridDesc* gd, int6
   return MRI_OK;
 }
 
-// hashdecoder_fwd.cu: tensor-core variant of the fused sweep (F = 2, L = 16, H = 64, D = 3 / 4, GELU / ReLU)
+// hashdecoder_fwd.cu / hashdecoder_fwd_geo.cu: tensor-core variant of the fused sweep (F = 2, L = 4 / 8 / 16, H = 64 / 128,
+// D = 3 / 4, GELU / ReLU)
 bool sweep_mma_supported(int dim, int n_levels, int n_features, int h, int act);
-int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int64_t first, int64_t count, const float* tables,
-                     const LevelTable& T, const float* decoder, int act, int last_act, float* out, cudaStream_t s);
+int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int n_levels, int h, int64_t first, int64_t count,
+                     const float* tables, const LevelTable& T, const float* decoder, int act, int last_act, float* out,
+                     cudaStream_t s);
 
 }  // namespace mri

@@ -16,6 +16,10 @@ inline bool fused_geometry_is_headline(int n_levels, int h) { return n_levels ==
 int launch_fused_fwd_geo(const float* x, int64_t n, int dim, int k0, int h, const float* tables, const LevelTable& T, const float* w1,
                          const float* b1, const float* w2, const float* b2, int act1, int act2, float* enc, float* y, float* pre2,
                          cudaStream_t s);
+struct GridDesc;
+int launch_sweep_mma_geo(const float* axes, const GridDesc& gd, int dim, int k0, int h, int64_t first, int64_t count,
+                         const float* tables, const LevelTable& T, const float* decoder, int act, int last_act, float* out,
+                         cudaStream_t s);
 int launch_fused_bwd_geo(const float* enc, int64_t n, int dim, int k0, int h, const float* w1, const float* b1, const float* w2,
                          const float* pre2, const float* gy, int act1, int act2, const float* x, const LevelTable& T, float* grad_tables,
                          float* gw1, float* gb1, float* gw2, float* gb2, int merge_nt2, cudaStream_t s);

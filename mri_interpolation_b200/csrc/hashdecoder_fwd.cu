@@ -27,51 +27,19 @@ bool geometry_ok(int dim, int n_levels, int n_features, int h, int act) {
 }  // namespace
 
 bool sweep_mma_supported(int dim, int n_levels, int n_features, int h, int act) {
-  return geometry_ok(dim, n_levels, n_features, h, act);
+  return fused_geometry_supported(dim, n_levels, n_features, h, act);
 }
 
-int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int64_t first, int64_t count, const float* tables,
-                     const LevelTable& T, const float* decoder, int act, int last_act, float* out, cudaStream_t s) {
-  constexpr int K0 = 32, H = 64;  // packed decoder: W1 (H x K0), b1 (H), w2 (H), b2 (1)
-  const float *w1 = decoder, *b1 = decoder + H * K0, *w2 = b1 + H, *b2 = w2 + H;
-  // whole axis-0 planes inside [first, first + count) are walked axis-0-fastest; a ragged head / tail (slab boundaries
-  // that cut a plane) keeps the C-order walk.  MRI_SWEEP_ORDER=c restores the C-order walk everywhere (A/B runs).
-  static const bool axis0_walk = [] { const char* e = getenv("MRI_SWEEP_ORDER"); return !(e && e[0] == 'c'); }();
-  int64_t plane = 1;
-  for (int d = 1; d < dim; ++d) plane *= gd.shape[d];
-  const int64_t p_begin = (first + plane - 1) / plane, p_end = (first + count) / plane;
-  const bool boxed = axis0_walk && p_end > p_begin && (p_end - p_begin) * plane < (int64_t{1} << 32);
-  const int64_t head = boxed ? p_begin * plane - first : count;
-  const int64_t box = boxed ? (p_end - p_begin) * plane : 0;
-  const int64_t tail = count - head - box;
-#define CALL_C(DV, ACTV, FIRST, COUNT, OUT)                                                                              \
-  launch_fused_fwd<DV, 32, 64, ACTV>(SweepCoords<DV>{axes, gd, FIRST}, COUNT, tables, T, w1, b1, w2, b2, ACTV, last_act, nullptr, OUT, \
-                             nullptr, s)
-#define CALL_B(DV, ACTV)                                                                                                          \
-  launch_fused_fwd<DV, 32, 64, ACTV>(SweepCoordsAxis0<DV>{axes, gd, head, static_cast<uint32_t>(p_begin), static_cast<uint32_t>(p_end - p_begin)}, \
-                             box, tables, T, w1, b1, w2, b2, ACTV, last_act, nullptr, out, nullptr, s)
-#define RUN(CALLEXPR)                              \
-  do {                                             \
-    const int st_ = (CALLEXPR);                    \
-    if (st_ != MRI_OK) return st_;                 \
-  } while (0)
-#define DISPATCH(DV, ACTV)                                                              \
-  do {                                                                                  \
-    if (head > 0) RUN(CALL_C(DV, ACTV, first, head, out));                              \
-    if (box > 0) RUN(CALL_B(DV, ACTV));                                                 \
-    if (tail > 0) RUN(CALL_C(DV, ACTV, first + head + box, tail, out + head + box));    \
-    return MRI_OK;                                                                      \
-  } while (0)
-  if (dim == 3) {
-    if (act == MRI_ACT_GELU) DISPATCH(3, MRI_ACT_GELU);
-    DISPATCH(3, MRI_ACT_RELU);
-  }
-  if (act == MRI_ACT_GELU) DISPATCH(4, MRI_ACT_GELU);
-  DISPATCH(4, MRI_ACT_RELU);
-#undef DISPATCH
-#undef RUN
-#undef CALL_B
-#undef CALL_C
+int launch_sweep_mma(const float* axes, const GridDesc& gd, int dim, int n_levels, int h, int64_t first, int64_t count,
+                     const float* tables, const LevelTable& T, const float* decoder, int act, int last_act, float* out,
+                     cudaStream_t s) {
+  if (!fused_geometry_is_headline(n_levels, h))  // the other F = 2 geometries: hashdecoder_fwd_geo.cu
+    return launch_sweep_mma_geo(axes, gd, dim, 2 * n_levels, h, first, count, tables, T, decoder, act, last_act, out, s);
+  if (dim == 3)
+    return act == MRI_ACT_GELU ? sweep_fused<3, 32, 64, MRI_ACT_GELU>(axes, gd, first, count, tables, T, decoder, act, last_act, out, s)
+                               : sweep_fused<3, 32, 64, MRI_ACT_RELU>(axes, gd, first, count, tables, T, decoder, act, last_act, out, s);
+  return act == MRI_ACT_GELU ? sweep_fused<4, 32, 64, MRI_ACT_GELU>(axes, gd, first, count, tables, T, decoder, act, last_act, out, s)
+                             : sweep_fused<4, 32, 64, MRI_ACT_RELU>(axes, gd, first, count, tables, T, decoder, act, last_act, out, s);
 }
 
 }  // namespace mri

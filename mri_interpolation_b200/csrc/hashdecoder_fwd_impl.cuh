@@ -228,5 +228,35 @@ int launch_fused_fwd(const Coords& src, int64_t n, const float* tables, const Le
 }
 
 
+// Dense sweep of a slab [first, first + count) of the C-order voxel grid with the fused kernel: whole axis-0 planes inside
+// the slab are walked axis-0-fastest (SweepCoordsAxis0); a ragged head / tail (slab boundaries that cut a plane) keeps the
+// C-order walk.  MRI_SWEEP_ORDER=c restores the C-order walk everywhere (A/B runs).  Packed decoder: W1 (H x K0), b1 (H),
+// w2 (H), b2 (1).
+template <int D, int K0, int H, int ACT1>
+int sweep_fused(const float* axes, const GridDesc& gd, int64_t first, int64_t count, const float* tables, const LevelTable& T,
+                const float* decoder, int act1, int last_act, float* out, cudaStream_t s) {
+  const float *w1 = decoder, *b1 = decoder + H * K0, *w2 = b1 + H, *b2 = w2 + H;
+  static const bool axis0_walk = [] { const char* e = getenv("MRI_SWEEP_ORDER"); return !(e && e[0] == 'c'); }();
+  int64_t plane = 1;
+  for (int d = 1; d < D; ++d) plane *= gd.shape[d];
+  const int64_t p_begin = (first + plane - 1) / plane, p_end = (first + count) / plane;
+  const bool boxed = axis0_walk && p_end > p_begin && (p_end - p_begin) * plane < (int64_t{1} << 32);
+  const int64_t head = boxed ? p_begin * plane - first : count;
+  const int64_t box = boxed ? (p_end - p_begin) * plane : 0;
+  const int64_t tail = count - head - box;
+  int st = MRI_OK;
+  if (head > 0)
+    st = launch_fused_fwd<D, K0, H, ACT1>(SweepCoords<D>{axes, gd, first}, head, tables, T, w1, b1, w2, b2, act1, last_act, nullptr, out,
+                                          nullptr, s);
+  if (st == MRI_OK && box > 0)
+    st = launch_fused_fwd<D, K0, H, ACT1>(
+        SweepCoordsAxis0<D>{axes, gd, head, static_cast<uint32_t>(p_begin), static_cast<uint32_t>(p_end - p_begin)}, box, tables, T, w1,
+        b1, w2, b2, act1, last_act, nullptr, out, nullptr, s);
+  if (st == MRI_OK && tail > 0)
+    st = launch_fused_fwd<D, K0, H, ACT1>(SweepCoords<D>{axes, gd, first + head + box}, tail, tables, T, w1, b1, w2, b2, act1, last_act,
+                                          nullptr, out + head + box, nullptr, s);
+  return st;
+}
+
 }  // namespace
 }  // namespace mri

@@ -261,7 +261,7 @@ extern "C" int mri_hashmlp_sweep(const float* axes, const int32_t* host_shape, i
   const int H = host_dims[1];
   static const bool use_cuda_cores = getenv("MRI_SWEEP_CUDA_CORES") != nullptr;  // debugging/profiling switch
   if (!use_cuda_cores && sweep_mma_supported(dim, n_levels, n_features, H, act))
-    return launch_sweep_mma(axes, gd, dim, first, count, tables, T, decoder, act, last_act, out, s);
+    return launch_sweep_mma(axes, gd, dim, n_levels, H, first, count, tables, T, decoder, act, last_act, out, s);
 #define CALL(D, F) dispatch_h<D, F>(H, axes, gd, first, count, tables, T, n_levels, decoder, act, last_act, out, s)
   switch (dim * 16 + n_features) {
     case 2 * 16 + 1: return CALL(2, 1);

@@ -226,22 +226,26 @@ def test_prefetch_loader_yields_host_batches_in_order():
         assert torch.equal(x.cpu(), hx) and torch.equal(y.cpu(), hy)
 
 
-@pytest.mark.parametrize("dim,shape", [(4, (13, 11, 3, 7)), (3, (21, 19, 10))])
-def test_tensor_core_sweep_kernel_matches_model_forward_and_oracle(dim, shape):
-    """Headline geometry (L=16, F=2, hidden 64): mri_hashmlp_sweep takes the encoder+decoder tensor-core kernel with
-    coordinates synthesised from the voxel index; slabs start at arbitrary voxels and need not be multiples of 16."""
+@pytest.mark.parametrize("dim,shape,n_levels,hidden,base,finest", [
+    (4, (13, 11, 3, 7), 16, 64, 16, 200), (3, (21, 19, 10), 16, 64, 16, 200),
+    (3, (37, 19, 10), 8, 64, (8, 6, 4), (96, 72, 12)),  # the notebook's shape: L = 8, anisotropic V2 levels
+    (4, (32, 5, 3, 4), 16, 128, 16, 200), (3, (21, 19, 10), 4, 128, 16, 200), (4, (13, 11, 3, 7), 8, 128, 8, 300)])
+def test_tensor_core_sweep_kernel_matches_model_forward_and_oracle(dim, shape, n_levels, hidden, base, finest):
+    """F = 2 geometries (L in {4, 8, 16}, hidden in {64, 128}): mri_hashmlp_sweep takes the encoder+decoder tensor-core kernel
+    with coordinates synthesised from the voxel index; slabs start at arbitrary voxels and need not be multiples of 16."""
     from mri_interpolation_b200 import models, sweep
     from oracle import hashgrid, networks, sweep as osweep
     torch.manual_seed(11)
-    net = models.HashMLP(dim_in=dim, n_levels=16, n_features_per_level=2, log2_hashmap_size=12, base_resolution=16,
-                         finest_resolution=200, dim_hidden=64, dim_out=1, n_layers=2, batch_norm=False)
+    net = models.HashMLP(dim_in=dim, n_levels=n_levels, n_features_per_level=2, log2_hashmap_size=12, base_resolution=base,
+                         finest_resolution=finest, dim_hidden=hidden, dim_out=1, n_layers=2, batch_norm=False)
     gen = torch.Generator().manual_seed(2)
     with torch.no_grad():
         for lv in net.encoder.levels:
             lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.3)
     params = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    levels = hashgrid.geometry(dim, 16, 12, 16, 200)
-    ref = osweep.dense_sweep(lambda c: networks.hashmlp_forward(c, params, levels, 2, False), shape, 1000)
+    levels = hashgrid.geometry(dim, n_levels, 12, base, finest)
+    aniso = not isinstance(base, int)
+    ref = osweep.dense_sweep(lambda c: networks.hashmlp_forward(c, params, levels, 2, aniso), shape, 1000)
     net = net.to(DEV)
     assert sweep._fused_plan(net) is not None
     fused = sweep.dense_sweep(net, shape)
