@@ -303,3 +303,43 @@ def test_fold_batchnorm_equals_linear_then_eval_batchnorm():
         torch.testing.assert_close(torch.nn.functional.linear(x, w, b), bn(lin(x)), rtol=1e-5, atol=1e-5)
     w, b = fold_batchnorm(lin, None)
     assert w is lin.weight and b is lin.bias
+
+
+def test_tensor_core_width_padding_rule():
+    """siren_fused.padded_width: multiples of 128 run as they are, other widths >= 160 are zero-padded to the next
+    multiple (the notebook's 352 -> 384), narrower ones stay on the fp32 path (0)."""
+    from mri_interpolation_b200 import siren_fused
+    assert [siren_fused.padded_width(h) for h in (128, 256, 1024)] == [128, 256, 1024]
+    assert siren_fused.padded_width(352) == 384 and siren_fused.padded_width(200) == 256 and siren_fused.padded_width(160) == 256
+    assert siren_fused.padded_width(64) == 0 and siren_fused.padded_width(159) == 0
+
+
+def test_fused_step_declines_what_it_cannot_serve_on_cpu():
+    """HashMLP.fused_training_step returns None (caller falls back to training_step + backward) for CPU batches; the
+    decoder plan accepts exactly 2 Linear+activation blocks with one output."""
+    torch.manual_seed(0)
+    net = models.HashMLP(dim_in=3, n_levels=4, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4,
+                         finest_resolution=16, dim_hidden=64, dim_out=1, n_layers=2, batch_norm=False)
+    assert net.fused_training_step((torch.rand(10, 3), torch.rand(10, 1)), 0) is None
+    plan = net._fused_decoder_plan()
+    assert plan is not None and plan[0].out_features == 64 and plan[1].out_features == 1
+    bn = models.HashMLP(dim_in=3, n_levels=4, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4,
+                        finest_resolution=16, dim_hidden=64, dim_out=1, n_layers=2, batch_norm=True)
+    assert bn._fused_decoder_plan() is None  # BatchNorm blocks: no one-kernel path
+    three = models.HashMLP(dim_in=3, n_levels=4, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4,
+                           finest_resolution=16, dim_hidden=64, dim_out=1, n_layers=3, batch_norm=False)
+    assert three._fused_decoder_plan() is None
+
+
+def test_spectral_norm_variant_wraps_every_linear_like_the_legacy_recipe():
+    """legacy_code/hash_experimentation.py:213-246: spectral_norm(Linear, n_power_iterations=4) in every block, Adam
+    with weight_decay; state_dict carries the parametrization's original weight and the u / v vectors."""
+    torch.manual_seed(0)
+    net = models.HashMLP(dim_in=3, n_levels=4, n_features_per_level=2, log2_hashmap_size=8, base_resolution=4,
+                         finest_resolution=16, dim_hidden=16, dim_out=1, n_layers=2, spectral_norm=True, weight_decay=1e-5)
+    keys = list(net.decoder.state_dict())
+    assert "0.0.parametrizations.weight.original" in keys and "0.0.parametrizations.weight.0._u" in keys
+    lin = net.decoder[0][0]
+    w = lin.weight
+    assert abs(float(torch.linalg.matrix_norm(w.detach(), ord=2)) - 1.0) < 0.2  # W / sigma after 4 power iterations
+    assert net.weight_decay == 1e-5 and isinstance(net.decoder[0][1], torch.nn.BatchNorm1d)
