@@ -761,3 +761,38 @@ def test_direct_step_equals_the_autograd_loop_over_several_optimiser_steps(n_lev
     assert direct.fused_training_step((x, torch.rand(100, 1, device=DEV)), 0) is None
     direct.criterion = torch.nn.functional.l1_loss
     assert direct.fused_training_step((x.detach(), torch.rand(100, 1, device=DEV)), 0) is None
+
+
+def test_locality_ordered_and_shuffled_batches_train_to_the_same_parameters():
+    """The batch ORDER is the loader's choice, the batch SET is the reference's: five Adam steps on locality-ordered
+    batches (axis-0 index fastest, what ShuffledEpochs produces) and on the same batches in random order end in the same
+    parameters up to fp32 summation order (G4-shaped model on a small volume, headline kernels with the register merge)."""
+    import copy
+    from mri_interpolation_b200 import functional as Fn, models
+    from mri_interpolation_b200.pl_compat import training_step_and_backward
+    kw = dict(dim_in=4, n_levels=16, n_features_per_level=2, log2_hashmap_size=14, base_resolution=16, finest_resolution=512,
+              dim_hidden=64, dim_out=1, n_layers=2)
+    torch.manual_seed(1337)
+    net = models.HashMLP(**kw, batch_norm=False, lr=5e-3)
+    gen = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for lv in net.encoder.levels:
+            lv.embedding.weight.copy_(torch.randn(lv.embedding.weight.shape, generator=gen) * 0.1)
+    shape = (48, 40, 4, 5)
+    total = int(np.prod(shape))
+    pix = torch.rand(total, generator=gen).to(DEV)
+    sampler = Fn.VoxelSampler(pix, shape)
+    a, b = copy.deepcopy(net).to(DEV), copy.deepcopy(net).to(DEV)
+    oa, ob = a.configure_optimizers(), b.configure_optimizers()
+    for step in range(5):
+        idx = torch.randperm(total, generator=gen)[:6000]
+        sorted_idx = Fn.locality_sort(idx, shape, block=1).to(DEV)
+        shuffled_idx = idx[torch.randperm(6000, generator=gen)].to(DEV)
+        assert torch.equal(torch.sort(sorted_idx).values, torch.sort(shuffled_idx).values)
+        la = training_step_and_backward(a, sampler.batch(sorted_idx), step)
+        lb = training_step_and_backward(b, sampler.batch(shuffled_idx), step)
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(lb))
+        oa.step(); oa.zero_grad(); ob.step(); ob.zero_grad()
+    for (k, p), (_, q) in zip(a.state_dict().items(), b.state_dict().items()):
+        if p.dtype.is_floating_point and p.numel() and float(q.norm()) > 0:
+            assert rel_err(p, q) < 1e-5, k
