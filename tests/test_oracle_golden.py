@@ -123,3 +123,32 @@ def test_metrics_sanity():
     frames = np.stack([np.full((2, 2), float(t)) for t in range(4)], -1)
     up = sweep.linear_time_interpolation(frames, 7)
     assert np.allclose(up[0, 0], np.linspace(0, 3, 7))
+
+
+def test_ssim_closed_form_known_answers():
+    """skimage is absent, so the SSIM restatement is pinned against cases with a closed form (skimage's definition,
+    K1 = 0.01, K2 = 0.03, data_range 1): identical images -> 1; two constant images A, B -> (2AB + c1) / (A^2 + B^2 + c1)
+    (zero variances and covariance); b = -a + 1 around mean 1/2 with small variance -> the luminance and contrast terms
+    separately computable."""
+    from oracle import sweep as osweep
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    rng = np.random.default_rng(0)
+    a = rng.random((20, 18)).astype(np.float32)
+    assert osweep.ssim2d(a, a) == pytest.approx(1.0, abs=1e-12)
+    A, B = 0.3, 0.7
+    got = osweep.ssim2d(np.full((15, 15), A, np.float32), np.full((15, 15), B, np.float32))
+    assert got == pytest.approx((2 * A * B + c1) / (A * A + B * B + c1), rel=1e-6)
+    # anti-correlated pair with equal means and variances: covariance = -variance inside every window
+    x = (rng.random((16, 16)) - 0.5).astype(np.float64) * 0.2
+    a2, b2 = (0.5 + x).astype(np.float32), (0.5 - x).astype(np.float32)
+    from scipy.ndimage import uniform_filter
+    win, n = 7, 49
+    m = uniform_filter(a2.astype(np.float64), win)
+    mb = uniform_filter(b2.astype(np.float64), win)
+    va = (uniform_filter(a2.astype(np.float64) ** 2, win) - m * m) * n / (n - 1)
+    vb = (uniform_filter(b2.astype(np.float64) ** 2, win) - mb * mb) * n / (n - 1)
+    cov = (uniform_filter(a2.astype(np.float64) * b2.astype(np.float64), win) - m * mb) * n / (n - 1)
+    assert np.allclose(cov[3:-3, 3:-3], -np.sqrt(va * vb)[3:-3, 3:-3], rtol=1e-4, atol=1e-9)
+    want = (((2 * m * mb + c1) * (2 * cov + c2)) / ((m * m + mb * mb + c1) * (va + vb + c2)))[3:-3, 3:-3].mean()
+    assert osweep.ssim2d(a2, b2) == pytest.approx(want, rel=1e-9)
+    assert osweep.ssim2d(a2, b2) < 0.0  # strongly anti-correlated structure
