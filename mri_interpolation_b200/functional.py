@@ -355,8 +355,8 @@ def _grad_buffer(p: torch.Tensor) -> torch.Tensor:
 def hashmlp_mse_direct_step(x: torch.Tensor, target: torch.Tensor, grid, w1, b1, w2, b2, act1: int, act2: int):
     """training_step + loss.backward() of HashMLP under the MSE loss WITHOUT the autograd engine: the three kernels the
     autograd path launches (mri_hashdecoder_forward, mri_mse_loss_grad, mri_hashdecoder_backward) called back to back,
-    gradients accumulated into the parameters' .grad buffers.  Same kernels, same arithmetic, bit-identical results - but
-    ~0.15 ms of Python per step instead of ~0.6 ms (two autograd Functions, the engine's worker-thread hand-off and the
+    gradients accumulated into the parameters' .grad buffers.  Same kernels, same arithmetic, results identical up to the
+    order in which the atomic reductions land - but ~0.15 ms of Python per step instead of ~0.6 ms (two autograd Functions, the engine's worker-thread hand-off and the
     loss-gradient multiply), which is what makes the launcher's loop GPU-bound at 2^19 coordinates per step."""
     n_levels, nf, dim = grid.n_levels, grid.n_features_per_level, grid.dim
     x2 = _lib.require_cuda_f32(x, "hashgrid input").reshape(-1, dim).contiguous()
