@@ -343,3 +343,24 @@ def test_spectral_norm_variant_wraps_every_linear_like_the_legacy_recipe():
     w = lin.weight
     assert abs(float(torch.linalg.matrix_norm(w.detach(), ord=2)) - 1.0) < 0.2  # W / sigma after 4 power iterations
     assert net.weight_decay == 1e-5 and isinstance(net.decoder[0][1], torch.nn.BatchNorm1d)
+
+
+def test_multiply_based_modulo_formula_is_exact():
+    """The arithmetic of csrc/common.cuh::exact_mod, replayed with numpy uint64: r = h - mulhi(h, floor(2^32 / rows)) * rows,
+    one conditional subtraction - equal to h % rows for every 32-bit h and every non-power-of-two row count up to 2^31
+    (the GPU tests assert the same on the kernels' own output)."""
+    rng = np.random.default_rng(0)
+    rows_list = [3, 5, 9, 81, 1000, 4489, 234256, 2247001, 3307949, (1 << 31) - 1, (1 << 31) - 19, (1 << 30) + 7]
+    rows_list += [int(v) for v in rng.integers(3, 1 << 31, 200)]
+    edge = np.array([0, 1, 2, (1 << 32) - 1, (1 << 32) - 2, 1 << 31, (1 << 31) - 1], dtype=np.uint64)
+    for rows in rows_list:
+        if rows & (rows - 1) == 0:
+            continue
+        magic = np.uint64((1 << 32) // rows)
+        h = np.concatenate([edge, rng.integers(0, 1 << 32, 4000, dtype=np.uint64),
+                            (np.arange(-3, 4, dtype=np.int64) + rows * rng.integers(1, max(2, (1 << 32) // rows), 50)[:, None]).reshape(-1).astype(np.uint64) & np.uint64(0xFFFFFFFF)])
+        q = (h * magic) >> np.uint64(32)
+        r = (h - q * np.uint64(rows)) & np.uint64(0xFFFFFFFF)
+        assert (r < 2 * rows).all()
+        r = np.where(r >= rows, r - np.uint64(rows), r)
+        assert (r == h % np.uint64(rows)).all(), rows
