@@ -119,9 +119,11 @@ def main(argv=None):
         t0 = time.time()
         local = sweep.dense_sweep(model, shape, batch_size=max(cfg.batch_size, 1 << 20), rank=rank, world_size=world)
         interp_im = sweep.gather_slabs(local, shape)
+        t_sweep = time.time() - t0
         if rank == 0:
             nifti.save(np.asarray(interp_im, dtype=np.float32), filepath + f"interpolation{tuple(shape)}.nii.gz")
-            print(f"interpolation {tuple(shape)}: {int(np.prod(shape)) / (time.time() - t0) / 1e6:.1f} Mvoxel/s incl. host gather")
+            print(f"interpolation {tuple(shape)}: {int(np.prod(shape)) / t_sweep / 1e6:.1f} Mvoxel/s incl. host gather, "
+                  f"{time.time() - t0 - t_sweep:.1f} s to gzip and write the NIfTI")
 
     if rank == 0:
         cfg.export_to_txt(file_path=filepath)
